@@ -1,0 +1,154 @@
+/* libqcs -- C ABI of the B200 (sm_100a) state-vector engine behind the qcircuits Python API.
+ *
+ * The reference (grey-area/qcircuits v0.6.0) is pure Python/NumPy and has no FFI of its own;
+ * the drop-in boundary is its Python class API.  Each entry point below replaces the NumPy
+ * call site(s) named in its comment (file:line into the reference tree) and is what
+ * qcircuits_b200/_lib.py binds with ctypes (see INTEGRATION.md for the binding a maintainer
+ * of the reference would add).
+ *
+ * Conventions
+ *  - A state of n qubits is a flat device array of 2^n complex amplitudes, interleaved (re, im),
+ *    float (QCS_C64) or double (QCS_C128).  Flat bit b (0 = least significant) is qcircuits
+ *    qubit n-1-b (C-order axis 0 = qubit 0 = most significant bit; reference state.py:60,111).
+ *  - Gate matrices are HOST pointers to 2^k x 2^k complex doubles, row-major, interleaved
+ *    (re, im), exactly Operator.to_matrix() (operators.py:75-93).  Operator qubit j (MSB-first
+ *    in the matrix index) acts on flat bit bitpos[j].
+ *  - Lazy normalisation.  The reference renormalises after every Operator(State)
+ *    (operators.py:275-276 -> state.py:97).  Here a buffer is paired with a device double
+ *    "norm2" holding the squared norm of its contents; the represented state is
+ *    buf / sqrt(norm2).  Kernels take `norm_in` (device pointer or NULL = 1.0), fold
+ *    1/sqrt(*norm_in) into their arithmetic, and write the squared norm of what they produced
+ *    to `norm_out` (device pointer or NULL), so no extra pass over the amplitudes is needed.
+ *  - libqcs never allocates or frees amplitude memory.  `ws` is a caller-owned, zero-initialised
+ *    device scratch of at least qcs_workspace_bytes() bytes; calls that share a `ws` must be
+ *    stream-ordered.  All calls are asynchronous on `stream` (a cudaStream_t).
+ *  - Every function returns 0 on success or a negative QCS_ERR_* code; qcs_last_error() gives
+ *    a thread-local message.  Nothing throws across the boundary.
+ */
+#ifndef QCS_H
+#define QCS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCS_OK 0
+#define QCS_ERR_ARG (-1)
+#define QCS_ERR_CUDA (-2)
+#define QCS_ERR_UNSUPPORTED (-3)
+
+#define QCS_C64 0  /* complex64  amplitudes (float2)  */
+#define QCS_C128 1 /* complex128 amplitudes (double2) */
+#define QCS_F64 2  /* real float64 input (marginals of a probability vector) */
+
+#define QCS_MAX_OP_QUBITS 4 /* largest gate the tile engine applies in one op   */
+#define QCS_MAX_OPS 64      /* ops per fused pass                                */
+
+#define QCS_OP_DENSE 0
+#define QCS_OP_DIAG 1
+
+/* One gate of a fused pass. */
+typedef struct qcs_op {
+    int32_t kind;                       /* QCS_OP_DENSE or QCS_OP_DIAG                                  */
+    int32_t k;                          /* operator qubits, 1..QCS_MAX_OP_QUBITS                         */
+    int32_t bitpos[QCS_MAX_OP_QUBITS];  /* flat bit each operator qubit acts on, MSB-first              */
+    uint64_t ctrl_mask;                 /* op acts only on indices i with (i & ctrl_mask) == ctrl_mask  */
+    const double *matrix;               /* host; DENSE: 2^k x 2^k complex, DIAG: the 2^k diagonal       */
+} qcs_op;
+
+typedef void *qcs_stream; /* cudaStream_t */
+
+int qcs_version(void);
+const char *qcs_last_error(void);
+int64_t qcs_workspace_bytes(void);
+
+/* Tile geometry for a fused pass (used by the host-side fusion scheduler).
+ * low_bits  : flat bits 0..low_bits-1 are always inside a tile (contiguous run staged in shared memory)
+ * tile_bits : at most tile_bits bits (low ones included) can be touched by dense ops of one pass */
+int qcs_tile_limits(int dtype, int *low_bits, int *tile_bits);
+
+/* Tuning hook (not a replacement for any reference call): 0 = cooperative load/store staging,
+ * 1 = TMA bulk-copy pipeline.  Also settable with the QCS_TILE_MODE=plain|bulk environment variable. */
+int qcs_set_tile_mode(int mode);
+
+/* K1/K3: Operator._apply on a State (operators.py:225-278): dst = M applied to src on bitpos,
+ * scaled by 1/sqrt(*norm_in); squared norm of dst to *norm_out.  k <= QCS_MAX_OP_QUBITS.
+ * dst may equal src (in-place). */
+int qcs_apply_gate(void *dst, const void *src, int n, int dtype, const double *matrix, int k,
+                   const int32_t *bitpos, const double *norm_in, double *norm_out, void *ws,
+                   qcs_stream stream);
+
+/* Same contraction for an operator of any size (k up to n), matrix already on the device in the
+ * amplitude dtype (2^k x 2^k, row-major).  Used for the "operator spans many qubits" case, e.g.
+ * the Grover iterate of examples/grover_algorithm.py:41,49.  dst must not alias src. */
+int qcs_apply_dense(void *dst, const void *src, int n, int dtype, const void *dev_matrix, int k,
+                    const int32_t *bitpos, const double *norm_in, double *norm_out, void *ws,
+                    qcs_stream stream);
+
+/* A run of gates fused into ONE pass over the state (north_star (1): "runs of adjacent gates fuse
+ * into one pass").  All dense ops' target bits >= low_bits must number at most
+ * tile_bits - low_bits (see qcs_tile_limits), else QCS_ERR_UNSUPPORTED.  Diagonal ops and control
+ * bits may sit anywhere.  Ops are applied in order. */
+int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
+                    const double *norm_in, double *norm_out, void *ws, qcs_stream stream);
+
+/* K5: State.probabilities (state.py:200): probs[i] = |src[i]|^2 / *norm_in ; sum to *sum_out. */
+int qcs_abs2(double *probs, const void *src, int n, int dtype, const double *norm_in,
+             double *sum_out, void *ws, qcs_stream stream);
+
+/* State.dot (state.py:89): out[0..1] = sum conj(a) * b (raw buffers, no lazy scale applied). */
+int qcs_dot(const void *a, const void *b, int n, int dtype, double *out2, void *ws, qcs_stream stream);
+
+/* State.renormalize_ / scalar * and / (state.py:97,174-185): dst = (re + i im)/sqrt(*norm_in) * src. */
+int qcs_scale(void *dst, const void *src, int n, int dtype, double re, double im,
+              const double *norm_in, double *norm_out, void *ws, qcs_stream stream);
+
+/* State + State, State - State, DensityOperator.from_ensemble accumulation (state.py:165-169):
+ * dst = alpha/sqrt(*norm_a) * a + beta/sqrt(*norm_b) * b  (alpha, beta complex, host). */
+int qcs_lincomb(void *dst, const void *a, const void *b, int n, int dtype, const double *alpha2,
+                const double *beta2, const double *norm_a, const double *norm_b, double *norm_out,
+                void *ws, qcs_stream stream);
+
+/* K9: Tensor.tensor_product (tensors.py:76): dst[(i << nb) | j] = a[i] * b[j] (a's qubits high). */
+int qcs_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype,
+             const double *norm_a, const double *norm_b, double *norm_out, void *ws, qcs_stream stream);
+
+/* K4: np.transpose relabelling (state.py:117,162): dst bit src_bit_of_dst_bit[b] <- ...:
+ * dst[i] = src[j] where bit src_bit[b] of j equals bit b of i. */
+int qcs_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t *src_bit,
+                     qcs_stream stream);
+
+/* State factories zeros/ones/bitstring (state.py:455-551): buf = 0 except buf[index] = 1. */
+int qcs_set_basis(void *buf, int n, int dtype, uint64_t index, qcs_stream stream);
+
+/* K6: State._measurement_probabilities (state.py:262-269): float64 marginals over the m listed
+ * bits (bitpos[0] = MSB of the outcome), divided by *norm_in.  dtype may be QCS_F64 (src is a
+ * real probability vector; used for DensityOperator marginals, density_operator.py:140-147).
+ * probs_out has 2^m doubles and is overwritten. */
+int qcs_marginal_probs(double *probs_out, const void *src, int n, int dtype, const int32_t *bitpos,
+                       int m, const double *norm_in, void *ws, int64_t ws_bytes, qcs_stream stream);
+
+/* K8: the collapse of State.measure (state.py:368-378): keep the amplitudes whose bits at bitpos
+ * equal `outcome` (bitpos[0] <-> MSB of outcome), times `scale`.  remove != 0: dst has n-m qubits
+ * (surviving bits keep their order); remove == 0: dst has n qubits, zero elsewhere.
+ * Squared norm of dst to *norm_out.  dst must not alias src when remove != 0. */
+int qcs_collapse(void *dst, const void *src, int n, int dtype, const int32_t *bitpos, int m,
+                 uint64_t outcome, int remove, double scale, double *norm_out, void *ws,
+                 qcs_stream stream);
+
+/* K11: DensityOperator.probabilities (density_operator.py:60): probs[i] = Re rho[i, i] for the
+ * interleaved rank-2n tensor (row bit of qubit q = flat bit 2(n-1-q)+1, column bit 2(n-1-q)). */
+int qcs_diag_probs(double *probs, const void *rho, int n, int dtype, double *sum_out, void *ws,
+                   qcs_stream stream);
+
+/* K13: DensityOperator.from_ensemble (density_operator.py:106-125):
+ * rho[interleave(r, c)] (+)= p / *norm_psi * psi[r] * conj(psi[c]);  accumulate != 0 adds. */
+int qcs_outer_accumulate(void *rho, const void *psi, int n, int dtype, double p,
+                         const double *norm_psi, int accumulate, qcs_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCS_H */

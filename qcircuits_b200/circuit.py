@@ -1,0 +1,201 @@
+"""Circuit: a gate list with a fusion scheduler (north_star (1): "runs of adjacent
+gates fuse into one pass").
+
+``Operator.__call__`` is one pass over the state per gate.  A Circuit collects the same
+``(operator, qubit_indices)`` pairs and reorders / groups them -- only across gates that commute --
+into passes that each fit one tile of the libqcs tile engine (include/qcs.h, qcs_apply_fused):
+every dense target of a pass lies in the low ``low_bits`` flat bits or in a small set of high bits
+chosen per pass; diagonal gates and control bits ride along wherever they sit.  The result is
+identical to applying the gates one by one (up to floating-point reassociation of the lazy
+normalisation) and is checked against the oracle in tests/.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._device import DeviceVector, make_ops
+from .state import State
+
+
+class _Gate:
+    __slots__ = ('plan', 'bits', 'nd_mask', 'd_mask', 'entries', 'wide', 'op')
+
+    def __init__(self, op, bits):
+        plan = op._plan()
+        self.op, self.plan, self.bits = op, plan, bits
+        tmask = 0
+        for q in plan.targets:
+            tmask |= 1 << bits[q]
+        cmask = 0
+        for q in plan.controls:
+            cmask |= 1 << bits[q]
+        # bits the gate acts on non-diagonally / diagonally (controls are diagonal on their bit)
+        self.nd_mask = 0 if plan.diagonal else tmask
+        self.d_mask = cmask | (tmask if plan.diagonal else 0)
+        t = len(plan.targets)
+        self.entries = (1 << t) if plan.diagonal else (1 << (2 * t))
+        self.wide = t > _lib.QCS_MAX_OP_QUBITS
+
+
+class Circuit:
+    """An ordered list of gates on ``n`` qubits.
+
+    >>> c = Circuit(3)
+    >>> c.append(qc.Hadamard(), [0]); c.append(qc.CNOT(), [0, 1])
+    >>> out = c.run(qc.zeros(3))            # == CNOT(H(zeros, [0]), [0, 1])
+    """
+
+    def __init__(self, n):
+        self.n = int(n)
+        self.gates = []
+        self._plans = {}
+
+    def append(self, op, qubit_indices=None):
+        from .operators import _validated_indices
+        qi = _validated_indices(op.rank // 2, self.n, qubit_indices)
+        self.gates.append(_Gate(op, [self.n - 1 - q for q in qi]))
+        self._plans.clear()
+        return self
+
+    def __len__(self):
+        return len(self.gates)
+
+    # -- scheduling ------------------------------------------------------------------------------------
+    def schedule(self, dtype=np.complex128, fuse=True, max_ops=24, lookahead=512):
+        """Group the gates into passes.  Returns a list of lists of gate indices (execution order
+        inside a pass = list order).  ``fuse=False`` gives one pass per gate."""
+        n = self.n
+        if not fuse:
+            return [[i] for i in range(len(self.gates))]
+        low, tile = ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.load().qcs_tile_limits(_lib.dtype_code(dtype), ctypes.byref(low), ctypes.byref(tile)))
+        L = min(low.value, n)
+        hcap = max(0, min(tile.value - low.value, n - L))
+        low_mask = (1 << L) - 1
+        pool_cap = 20480 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
+        max_ops = min(max_ops, _lib.QCS_MAX_OPS)
+        gates = self.gates
+        remaining = list(range(len(gates)))
+        passes = []
+
+        def scan(tile_mask, commit):
+            blk_nd = blk_d = 0
+            taken, entries = [], 0
+            full = (1 << n) - 1
+            for idx in remaining[:lookahead]:
+                g = gates[idx]
+                ok = (not g.wide and (g.nd_mask & ~tile_mask) == 0 and (g.nd_mask & (blk_nd | blk_d)) == 0
+                      and (g.d_mask & blk_nd) == 0 and len(taken) < max_ops and entries + g.entries <= pool_cap)
+                if ok:
+                    taken.append(idx)
+                    entries += g.entries
+                else:
+                    blk_nd |= g.nd_mask
+                    blk_d |= g.d_mask
+                    if blk_nd == full:
+                        break
+            return taken
+
+        while remaining:
+            first = gates[remaining[0]]
+            if first.wide:                      # operator wider than the tile engine: its own dense pass
+                passes.append([remaining.pop(0)])
+                continue
+            candidates = [low_mask]
+            for s in range(L, n - hcap + 1):
+                candidates.append(low_mask | (((1 << hcap) - 1) << s))
+            # the first pending gate must always be schedulable: its own high bits, padded upwards
+            need = first.nd_mask & ~low_mask
+            if need:
+                m, b = need, L
+                while bin(m).count('1') < hcap and b < n:
+                    m |= 1 << b
+                    b += 1
+                if bin(need).count('1') <= hcap:
+                    while bin(m).count('1') > hcap:
+                        extra = (m & ~need)
+                        m &= ~(extra & -extra)
+                    candidates.append(low_mask | m)
+            best, best_mask = None, None
+            for mask in candidates:
+                taken = scan(mask, False)
+                if best is None or len(taken) > len(best):
+                    best, best_mask = taken, mask
+            if not best:
+                # a gate whose dense targets exceed one tile even alone: give it the tile it needs
+                best = [remaining[0]]
+            passes.append(best)
+            chosen = set(best)
+            remaining = [i for i in remaining if i not in chosen]
+        return passes
+
+    def _compiled(self, dtype, fuse, max_ops):
+        key = (np.dtype(dtype).str, fuse, max_ops)
+        comp = self._plans.get(key)
+        if comp is None:
+            comp = []
+            for group in self.schedule(dtype, fuse=fuse, max_ops=max_ops):
+                g0 = self.gates[group[0]]
+                if g0.wide:
+                    comp.append(('dense', g0))
+                else:
+                    ops, keep = make_ops([(self.gates[i].plan, self.gates[i].bits, False) for i in group])
+                    comp.append(('tile', ops, keep, len(group)))
+            self._plans[key] = comp
+        return comp
+
+    # -- execution ---------------------------------------------------------------------------------------
+    def run(self, state, fuse=True, max_ops=24):
+        """Apply the circuit to ``state`` and return the new State; the argument is left untouched
+        (the first pass writes a fresh buffer, later passes update it in place)."""
+        if state.rank != self.n:
+            raise ValueError('circuit and state have different numbers of qubits')
+        src = state._dv
+        if not self.gates:
+            return State(src.clone())
+        lib = _lib.load()
+        ws = _lib.workspace().data_ptr()
+        stream = _lib.stream_ptr()
+        code = src.code
+        cur = DeviceVector(_lib.alloc_amplitudes(src.nbits, src.dtype), None, src.nbits, src.dtype)
+        norms = [_lib.alloc_scalar(), _lib.alloc_scalar()]
+        norm_in = None if src.norm is None else src.norm.data_ptr()
+        src_ptr, which = src.buf.data_ptr(), 0
+        for item in self._compiled(src.dtype, fuse, max_ops):
+            norm_out = norms[which].data_ptr()
+            if item[0] == 'tile':
+                _lib.check(lib.qcs_apply_fused(cur.buf.data_ptr(), src_ptr, self.n, code, item[1], len(item[1]),
+                                               norm_in, norm_out, ws, stream))
+            else:
+                g = item[1]
+                if src_ptr == cur.buf.data_ptr():      # the dense path is out of place
+                    tmp = cur.buf.clone()
+                    src_ptr = tmp.data_ptr()
+                _lib.check(lib.qcs_apply_dense(cur.buf.data_ptr(), src_ptr, self.n, code,
+                                               g.op._device_matrix(src.dtype).data_ptr(), g.plan.k,
+                                               _lib.int32_array(g.bits), norm_in, norm_out, ws, stream))
+            src_ptr, norm_in = cur.buf.data_ptr(), norm_out
+            cur.norm = norms[which]
+            which ^= 1
+        return State(cur)
+
+    def run_host(self, host_in, host_out, fuse=True, max_ops=24):
+        """Host-buffer entry: ``host_in`` / ``host_out`` are (pinned) torch CPU tensors holding 2^n
+        complex amplitudes (complex64/complex128 or interleaved reals).  Copies the state to the
+        device, runs the circuit, copies the normalised result back.  Returns ``host_out``."""
+        t = _lib.require_cuda()
+        real_in = t.view_as_real(host_in).reshape(-1) if host_in.is_complex() else host_in.reshape(-1)
+        real_out = t.view_as_real(host_out).reshape(-1) if host_out.is_complex() else host_out.reshape(-1)
+        np_dtype = np.complex64 if real_in.dtype == t.float32 else np.complex128
+        dev = _lib.alloc_amplitudes(self.n, np_dtype)
+        dev.copy_(real_in, non_blocking=True)
+        out = self.run(State(DeviceVector(dev, None, self.n, np_dtype)), fuse=fuse, max_ops=max_ops)
+        res = out._dv.scaled(1.0)            # fold the lazy 1/sqrt(norm) before leaving the device
+        real_out.copy_(res.buf, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return host_out
+
+    def stats(self, dtype=np.complex128, fuse=True, max_ops=24):
+        """(number of passes, number of gates) for the schedule used by run()."""
+        return len(self._compiled(dtype, fuse, max_ops)), len(self.gates)

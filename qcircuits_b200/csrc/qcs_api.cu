@@ -1,0 +1,190 @@
+// extern "C" surface of libqcs (include/qcs.h): argument checks, error strings, dispatch.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "qcs_common.cuh"
+#include "qcs_internal.h"
+
+namespace qcs {
+
+static thread_local char g_err[256] = "";
+
+int set_error(int code, const char *msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+const DeviceInfo &device_info() {
+    static thread_local DeviceInfo info[16];
+    static thread_local bool have[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) dev = 0;
+    if (!have[dev]) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int smem = 0;
+        cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        info[dev].sms = sms > 0 ? sms : 148;
+        info[dev].smem_per_sm = (size_t)smem;
+        have[dev] = true;
+    }
+    return info[dev];
+}
+
+static int g_tile_mode = -1;
+int tile_mode() {
+    if (g_tile_mode < 0) {
+        const char *e = std::getenv("QCS_TILE_MODE");
+        g_tile_mode = (e && std::strcmp(e, "plain") == 0)  ? TILE_MODE_PLAIN
+                      : (e && std::strcmp(e, "bulk") == 0) ? TILE_MODE_BULK
+                                                           : TILE_MODE_DEFAULT;
+    }
+    return g_tile_mode;
+}
+
+static int check_state(const void *p, int n, int dtype) {
+    if (!p) return set_error(QCS_ERR_ARG, "null amplitude pointer");
+    if (n < 1 || n > 40) return set_error(QCS_ERR_ARG, "qubit count must be in 1..40");
+    if (dtype != QCS_C64 && dtype != QCS_C128) return set_error(QCS_ERR_ARG, "dtype must be QCS_C64 or QCS_C128");
+    return QCS_OK;
+}
+
+}  // namespace qcs
+
+using namespace qcs;
+
+extern "C" {
+
+int qcs_version(void) { return 100; }
+const char *qcs_last_error(void) { return g_err; }
+int64_t qcs_workspace_bytes(void) { return WS_BYTES; }
+
+int qcs_set_tile_mode(int mode) {
+    if (mode != TILE_MODE_PLAIN && mode != TILE_MODE_BULK) return set_error(QCS_ERR_ARG, "tile mode must be 0 or 1");
+    g_tile_mode = mode;
+    return QCS_OK;
+}
+
+int qcs_tile_limits(int dtype, int *low_bits, int *tile_bits) {
+    if (dtype != QCS_C64 && dtype != QCS_C128) return set_error(QCS_ERR_ARG, "bad dtype");
+    if (low_bits) *low_bits = dtype == QCS_C64 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
+    if (tile_bits) *tile_bits = dtype == QCS_C64 ? TILE_MAX_BITS_C64 : TILE_MAX_BITS_C128;
+    return QCS_OK;
+}
+
+int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
+                    double *norm_out, void *ws, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(src, n, dtype)) return e;
+    if (!ops || nops < 1 || nops > QCS_MAX_OPS) return set_error(QCS_ERR_ARG, "op count must be in 1..QCS_MAX_OPS");
+    if (norm_out && !ws) return set_error(QCS_ERR_ARG, "norm_out needs a workspace");
+    for (int i = 0; i < nops; ++i)
+        if (!ops[i].matrix) return set_error(QCS_ERR_ARG, "op without a matrix");
+    return tile_apply(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_apply_gate(void *dst, const void *src, int n, int dtype, const double *matrix, int k, const int32_t *bitpos,
+                   const double *norm_in, double *norm_out, void *ws, qcs_stream stream) {
+    if (!matrix || !bitpos) return set_error(QCS_ERR_ARG, "null matrix or bit positions");
+    if (k < 1 || k > QCS_MAX_OP_QUBITS) return set_error(QCS_ERR_ARG, "qcs_apply_gate handles 1..4 operator qubits");
+    qcs_op op;
+    op.kind = QCS_OP_DENSE;
+    op.k = k;
+    for (int j = 0; j < QCS_MAX_OP_QUBITS; ++j) op.bitpos[j] = j < k ? bitpos[j] : 0;
+    op.ctrl_mask = 0;
+    op.matrix = matrix;
+    return qcs_apply_fused(dst, src, n, dtype, &op, 1, norm_in, norm_out, ws, stream);
+}
+
+int qcs_apply_dense(void *dst, const void *src, int n, int dtype, const void *dev_matrix, int k, const int32_t *bitpos,
+                    const double *norm_in, double *norm_out, void *ws, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(src, n, dtype)) return e;
+    if (!dev_matrix || !bitpos) return set_error(QCS_ERR_ARG, "null matrix or bit positions");
+    if (norm_out && !ws) return set_error(QCS_ERR_ARG, "norm_out needs a workspace");
+    return misc_dense(dst, src, n, dtype, dev_matrix, k, bitpos, norm_in, norm_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_abs2(double *probs, const void *src, int n, int dtype, const double *norm_in, double *sum_out, void *ws,
+             qcs_stream stream) {
+    if (int e = check_state(src, n, dtype)) return e;
+    if (sum_out && !ws) return set_error(QCS_ERR_ARG, "sum_out needs a workspace");
+    return misc_abs2(probs, src, n, dtype, norm_in, sum_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_dot(const void *a, const void *b, int n, int dtype, double *out2, void *ws, qcs_stream stream) {
+    if (int e = check_state(a, n, dtype)) return e;
+    if (int e = check_state(b, n, dtype)) return e;
+    if (!out2 || !ws) return set_error(QCS_ERR_ARG, "null output or workspace");
+    return misc_dot(a, b, n, dtype, out2, ws, (cudaStream_t)stream);
+}
+
+int qcs_scale(void *dst, const void *src, int n, int dtype, double re, double im, const double *norm_in,
+              double *norm_out, void *ws, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(src, n, dtype)) return e;
+    const double alpha[2] = {re, im};
+    return misc_lincomb(dst, src, nullptr, n, dtype, alpha, nullptr, norm_in, nullptr, norm_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_lincomb(void *dst, const void *a, const void *b, int n, int dtype, const double *alpha2, const double *beta2,
+                const double *norm_a, const double *norm_b, double *norm_out, void *ws, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(a, n, dtype)) return e;
+    if (int e = check_state(b, n, dtype)) return e;
+    if (!alpha2 || !beta2) return set_error(QCS_ERR_ARG, "null coefficient");
+    return misc_lincomb(dst, a, b, n, dtype, alpha2, beta2, norm_a, norm_b, norm_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype, const double *norm_a,
+             const double *norm_b, double *norm_out, void *ws, qcs_stream stream) {
+    if (int e = check_state(a, na, dtype)) return e;
+    if (int e = check_state(b, nb, dtype)) return e;
+    if (int e = check_state(dst, na + nb, dtype)) return e;
+    return misc_kron(dst, a, na, b, nb, dtype, norm_a, norm_b, norm_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(src, n, dtype)) return e;
+    if (!src_bit) return set_error(QCS_ERR_ARG, "null permutation");
+    if (dst == src) return set_error(QCS_ERR_ARG, "permute_bits cannot run in place");
+    return misc_permute(dst, src, n, dtype, src_bit, (cudaStream_t)stream);
+}
+
+int qcs_set_basis(void *buf, int n, int dtype, uint64_t index, qcs_stream stream) {
+    if (int e = check_state(buf, n, dtype)) return e;
+    return misc_set_basis(buf, n, dtype, index, (cudaStream_t)stream);
+}
+
+int qcs_marginal_probs(double *probs_out, const void *src, int n, int dtype, const int32_t *bitpos, int m,
+                       const double *norm_in, void *ws, int64_t ws_bytes, qcs_stream stream) {
+    if (!probs_out || !src || !bitpos || !ws) return set_error(QCS_ERR_ARG, "null pointer");
+    if (n < 1 || n > 40) return set_error(QCS_ERR_ARG, "qubit count must be in 1..40");
+    return misc_marginal(probs_out, src, n, dtype, bitpos, m, norm_in, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int qcs_collapse(void *dst, const void *src, int n, int dtype, const int32_t *bitpos, int m, uint64_t outcome,
+                 int remove, double scale, double *norm_out, void *ws, qcs_stream stream) {
+    if (int e = check_state(src, n, dtype)) return e;
+    if (!dst || !bitpos) return set_error(QCS_ERR_ARG, "null pointer");
+    if (norm_out && !ws) return set_error(QCS_ERR_ARG, "norm_out needs a workspace");
+    return misc_collapse(dst, src, n, dtype, bitpos, m, outcome, remove, scale, norm_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_diag_probs(double *probs, const void *rho, int n, int dtype, double *sum_out, void *ws, qcs_stream stream) {
+    if (!probs || !rho) return set_error(QCS_ERR_ARG, "null pointer");
+    if (dtype != QCS_C64 && dtype != QCS_C128) return set_error(QCS_ERR_ARG, "bad dtype");
+    return misc_diag_probs(probs, rho, n, dtype, sum_out, ws, (cudaStream_t)stream);
+}
+
+int qcs_outer_accumulate(void *rho, const void *psi, int n, int dtype, double p, const double *norm_psi,
+                         int accumulate, qcs_stream stream) {
+    if (!rho || !psi) return set_error(QCS_ERR_ARG, "null pointer");
+    if (dtype != QCS_C64 && dtype != QCS_C128) return set_error(QCS_ERR_ARG, "bad dtype");
+    return misc_outer(rho, psi, n, dtype, p, norm_psi, accumulate, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+"""Operator, OperatorBase and the gate factories -- the drop-in for reference
+qcircuits/operators.py.
+
+Gate tensors are parameters (at most 2^22 entries in any configuration), so they stay host
+NumPy arrays; Operator-on-Operator composition (operators.py:225-278 with an OperatorBase
+argument) is host arithmetic.  What changes is Operator-on-State and Operator-on-DensityOperator:
+those no longer run ``np.tensordot`` over the rank-n tensor but call the sm_100a kernels of
+libqcs (qcs_apply_fused / qcs_apply_dense) on the device buffer, with the reference's
+renormalise-after-every-gate folded into the same pass (see include/qcs.h, "lazy normalisation").
+"""
+from itertools import product
+
+import numpy as np
+
+from . import _gates
+from .tensors import Tensor
+
+
+def _pair_axes(qubit_order):
+    """axes of an interleaved operator tensor when its qubits are listed in qubit_order"""
+    return [a for q in qubit_order for a in (2 * q, 2 * q + 1)]
+
+
+class OperatorBase(Tensor):
+    """Common functionality of Operator and DensityOperator (reference operators.py:24-170)."""
+
+    def __init__(self, tensor):
+        super().__init__(tensor)
+
+    @staticmethod
+    def from_matrix(M):
+        """Matrix (Kronecker-product convention) -> Operator (operators.py:37-73)."""
+        if type(M) is list:
+            M = np.array(M, dtype=np.complex128)
+        if M.ndim != 2 or M.shape[0] != M.shape[1]:
+            raise ValueError('The matrix should be square.')
+        d = np.log2(M.shape[0])
+        if not float(d).is_integer():
+            raise ValueError('The matrix dimension should be a power of 2.')
+        d = int(d)
+        # matrix axes are (out_0..out_{d-1}, in_0..in_{d-1}); the tensor interleaves them
+        interleave = np.arange(2 * d).reshape(2, d).T.reshape(-1)
+        return Operator(np.reshape(M, [2] * (2 * d)).transpose(interleave))
+
+    @staticmethod
+    def _tensor_to_matrix(t):
+        d = t.ndim // 2
+        outs_then_ins = list(range(0, 2 * d, 2)) + list(range(1, 2 * d, 2))
+        return t.transpose(outs_then_ins).reshape(2 ** d, 2 ** d)
+
+    def to_matrix(self):
+        """Operator -> matrix (operators.py:81-93)."""
+        return self._tensor_to_matrix(self._t)
+
+    @property
+    def adj(self):
+        """Conjugate transpose: conjugate and swap every (out, in) axis pair (operators.py:95-114)."""
+        r = self.rank
+        swap_pairs = np.arange(r).reshape(r // 2, 2)[:, ::-1].reshape(-1)
+        return self.__class__(np.conj(self._t).transpose(swap_pairs))
+
+    def _permuted_tensor(self, axes, inverse=False):
+        if inverse:
+            axes = np.argsort(axes)
+        return np.transpose(self._t, _pair_axes(axes))
+
+    def permute_qubits(self, axes, inverse=False):
+        """Relabel the qubits (both wires of each); in place, returns self (operators.py:125-146)."""
+        self._t = self._permuted_tensor(axes, inverse=inverse)
+        return self
+
+    def swap_qubits(self, axis1, axis2):
+        """Swap two qubits (both wires); in place, returns self (operators.py:148-170)."""
+        order = list(range(self.rank // 2))
+        order[axis1], order[axis2] = order[axis2], order[axis1]
+        self._t = np.transpose(self._t, _pair_axes(order))
+        return self
+
+
+from .density_operator import DensityOperator  # noqa: E402  (circular by design, like the reference)
+from .state import State  # noqa: E402
+
+
+def _validated_indices(op_qubits, d, qubit_indices):
+    """The reference's argument checks, same order and exception type (operators.py:234-253)."""
+    if op_qubits > d:
+        raise ValueError('An operator for a d-rank state space can only be applied to '
+                         'a system whose rank is >= d.')
+    if op_qubits < d and qubit_indices is None:
+        raise ValueError('Applying operator to too-large system without supplying '
+                         'qubit indices.')
+    if qubit_indices is None:
+        return list(range(d))
+    qubit_indices = [int(q) for q in qubit_indices]
+    if len(set(qubit_indices)) != len(qubit_indices):
+        raise ValueError('Qubit indices list contains repeated elements.')
+    if min(qubit_indices) < 0:
+        raise ValueError('Supplied qubit index < 0.')
+    if max(qubit_indices) >= d:
+        raise ValueError('Supplied qubit index larger than system size.')
+    if len(qubit_indices) != op_qubits:
+        raise ValueError('Length of qubit_indices does not match operator.')
+    return qubit_indices
+
+
+class Operator(OperatorBase):
+    """An operator on the state space of d qubits: a rank-2d tensor, axes (out0, in0, out1, in1, ...)."""
+
+    def __init__(self, tensor):
+        super().__init__(tensor)
+        self._plan_cache = None       # structure analysis of the matrix (diagonal / controlled)
+        self._dev_matrix = {}         # dtype -> device copy, for operators wider than 4 qubits
+
+    def __repr__(self):
+        head = 'Operator('
+        return head + str(self._t).replace('\n', '\n' + ' ' * len(head)) + ')'
+
+    def __str__(self):
+        return 'Operator for {}-qubit state space. Tensor:\n{}'.format(self.rank // 2, self._t)
+
+    def __add__(self, arg):
+        return Operator(self._t + arg._t)
+
+    def __sub__(self, arg):
+        return self + (-1) * arg
+
+    def __neg__(self):
+        return Operator(-self._t)
+
+    def __mul__(self, scalar):
+        if isinstance(scalar, (float, int, complex)):
+            return Operator(scalar * self._t)
+        return super().__mul__(scalar)
+
+    def __rmul__(self, scalar):
+        if isinstance(scalar, (float, int, complex)):
+            return Operator(scalar * self._t)
+
+    def __truediv__(self, scalar):
+        return Operator(self._t / scalar)
+
+    # -- application ---------------------------------------------------------------------------
+    def _compose(self, arg, qubit_indices):
+        """A(B) for operator-shaped B on the host: contract this operator's in-wires with B's
+        out-wires on the chosen qubits (operators.py:226-274)."""
+        d = arg.rank // 2
+        k = self.rank // 2
+        qi = _validated_indices(k, d, qubit_indices)
+        order = qi + sorted(set(range(d)) - set(qi))
+        moved = np.transpose(arg._t, _pair_axes(order))
+        out = np.tensordot(self._t, moved, (list(range(1, 2 * k, 2)), list(range(0, 2 * k, 2))))
+        # tensordot yields (out_0..out_{k-1}, in_0..in_{k-1}, rest); restore the interleaving
+        back = np.concatenate([np.arange(2 * k).reshape(2, k).T.reshape(-1), np.arange(2 * k, 2 * d)])
+        result = arg.__class__(np.transpose(out, back))
+        return result.permute_qubits(order, inverse=True)
+
+    def _apply(self, arg, qubit_indices=None):
+        if isinstance(arg, State):
+            qi = _validated_indices(self.rank // 2, arg.rank, qubit_indices)
+            return arg._apply_operator(self, qi)
+        if isinstance(arg, DensityOperator):
+            qi = _validated_indices(self.rank // 2, arg.rank // 2, qubit_indices)
+            return arg._apply_operator(self, qi)
+        return self._compose(arg, qubit_indices)
+
+    def __call__(self, arg, qubit_indices=None):
+        """A(v) for a State, A rho A^dagger for a DensityOperator, A(B) composition for an
+        Operator; ``qubit_indices`` selects (and orders) the qubits of a larger system
+        (operators.py:280-323).  The argument is never modified."""
+        return self._apply(arg, qubit_indices)
+
+    def _device_matrix(self, dtype, conj=False):
+        """Device copy of the full matrix in the amplitude dtype (operators wider than 4 qubits)."""
+        from . import _lib
+        key = (np.dtype(dtype).str, conj, _lib.torch().cuda.current_device())
+        dev = self._dev_matrix.get(key)
+        if dev is None:
+            M = self._plan().full
+            dev = _lib.upload(np.conj(M) if conj else M, dtype)
+            self._dev_matrix[key] = dev
+        return dev
+
+    def _plan(self):
+        """Structure of the matrix, cached: see _gates.analyze."""
+        if self._plan_cache is None:
+            self._plan_cache = _gates.analyze(np.ascontiguousarray(self.to_matrix()))
+        return self._plan_cache
+
+
+# ---------------------------------------------------------------------------------------------------
+# gate factories (reference operators.py:328-853); matrices are the standard textbook ones
+# ---------------------------------------------------------------------------------------------------
+def _single(matrix, d):
+    return Operator(np.array(matrix, dtype=np.complex128)).tensor_power(d)
+
+
+def Identity(d=1):
+    """d-qubit identity."""
+    return _single([[1, 0], [0, 1]], d)
+
+
+def PauliX(d=1):
+    """X on each of d qubits (NOT)."""
+    return _single([[0, 1], [1, 0]], d)
+
+
+def PauliY(d=1):
+    """Y on each of d qubits: |0> -> i|1>, |1> -> -i|0>."""
+    return _single([[0, -1j], [1j, 0]], d)
+
+
+def PauliZ(d=1):
+    """Z on each of d qubits."""
+    return _single([[1, 0], [0, -1]], d)
+
+
+def Hadamard(d=1):
+    """H on each of d qubits."""
+    return _single(1 / np.sqrt(2) * np.array([[1.0 + 0.0j, 1.0 + 0.0j], [1.0 + 0.0j, -1.0 + 0.0j]]), d)
+
+
+def Phase(d=1):
+    """S = diag(1, i)."""
+    return _single([[1, 0], [0, 1j]], d)
+
+
+def PiBy8(d=1):
+    """T = diag(1, exp(i pi/4))."""
+    return _single([[1, 0], [0, np.exp(1j * np.pi / 4)]], d)
+
+
+def Rotation(v, theta):
+    """Rotation of the Bloch vector by theta about the real unit 3-vector v."""
+    v = np.array(v)
+    if v.shape != (3,) or abs(v.dot(v) - 1.0) > 1e-8 or not np.all(np.isreal(v)):
+        raise ValueError('Rotation vector v should be a 3D real unit vector.')
+    return np.cos(theta / 2) * Identity() - 1j * np.sin(theta / 2) * (
+        v[0] * PauliX() + v[1] * PauliY() + v[2] * PauliZ())
+
+
+def RotationX(theta):
+    return Rotation([1., 0., 0.], theta)
+
+
+def RotationY(theta):
+    return Rotation([0., 1., 0.], theta)
+
+
+def RotationZ(theta):
+    return Rotation([0., 0., 1.], theta)
+
+
+def SqrtNot(d=1):
+    """Square root of X."""
+    return _single(0.5 * np.array([[1 + 1j, 1 - 1j], [1 - 1j, 1 + 1j]]), d)
+
+
+def _from_basis_map(d, image_of):
+    """Permutation operator sending basis bit-tuple b to image_of(b)."""
+    t = np.zeros([2] * (2 * d), dtype=np.complex128)
+    for bits in product([0, 1], repeat=d):
+        out = image_of(bits)
+        t[tuple(x for pair in zip(out, bits) for x in pair)] = 1.0
+    return Operator(t)
+
+
+def CNOT():
+    """Flip the second qubit if the first is set."""
+    return _from_basis_map(2, lambda b: (b[0], b[1] ^ b[0]))
+
+
+def Toffoli():
+    """Flip the third qubit if the first two are set."""
+    return _from_basis_map(3, lambda b: (b[0], b[1], b[2] ^ (b[0] & b[1])))
+
+
+def Swap():
+    """Exchange two qubits."""
+    return _from_basis_map(2, lambda b: (b[1], b[0]))
+
+
+def SqrtSwap():
+    """Square root of Swap."""
+    p, m = 0.5 * (1 + 1j), 0.5 * (1 - 1j)
+    return OperatorBase.from_matrix(np.array([[1, 0, 0, 0], [0, p, m, 0], [0, m, p, 0], [0, 0, 0, 1]]))
+
+
+def ControlledU(U):
+    """(d+1)-qubit operator applying the d-qubit U when the first qubit is set."""
+    d = U.rank // 2 + 1
+    t = np.zeros([2] * (2 * d), dtype=np.complex128)
+    t[0, 0] = Identity(d - 1)._t
+    t[1, 1] = U._t
+    return Operator(t)
+
+
+def U_f(f, d):
+    """d-qubit operator flipping the last qubit when the Boolean f of the first d-1 bits is 1."""
+    if d < 2:
+        raise ValueError('U_f operator requires rank >= 2.')
+
+    def image(bits):
+        r = f(*bits[:-1])
+        if r not in [0, 1]:
+            raise RuntimeError('Function f for U_f operator should be Boolean,'
+                               'i.e., return 0 or 1.')
+        return bits[:-1] + ((1 - bits[-1]) if r else bits[-1],)
+
+    return _from_basis_map(d, image)

@@ -1,0 +1,70 @@
+"""CPU tests of the fusion scheduler: a schedule is a reordering of the gate list that only commutes
+gates past each other when that is exact, and every pass fits one tile."""
+import numpy as np
+import pytest
+
+import qcircuits_b200 as qc
+from oracle import qc_oracle as orc
+from qcircuits_b200.circuit import Circuit
+from tests.util import rand_state_vec, rand_unitary
+
+
+def _layered(n, depth, seed=1234):
+    mk = {'H': lambda t: qc.Hadamard(), 'RX': qc.RotationX, 'RZ': qc.RotationZ, 'CNOT': lambda t: qc.CNOT(),
+          'CZ': lambda t: qc.ControlledU(qc.PauliZ())}
+    c = Circuit(n)
+    for name, theta, qs in orc.layered_circuit(n, depth, seed):
+        c.append(mk[name](theta), list(qs))
+    return c
+
+
+def _run_oracle(circ, order, vec):
+    n = circ.n
+    for i in order:
+        g = circ.gates[i]
+        vec = orc.apply_matrix_flat(g.plan.full, vec, g.bits)
+    return vec
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_schedule_is_a_valid_reordering(dtype):
+    rng = np.random.default_rng(5)
+    n = 14
+    c = _layered(n, 6)
+    # a few awkward extras: wide gate, 3-qubit dense on high bits, reversed CNOT, swaps
+    c.append(qc.Operator.from_matrix(rand_unitary(rng, 5)), [0, 3, 6, 9, 12])
+    c.append(qc.Operator.from_matrix(rand_unitary(rng, 3)), [0, 1, 2])
+    c.append(qc.CNOT(), [7, 2])
+    c.append(qc.Swap(), [0, 13])
+    c.append(qc.Toffoli(), [1, 12, 5])
+    for name, theta, qs in orc.layered_circuit(n, 2, seed=9):
+        c.append({'H': qc.Hadamard(), 'RX': qc.RotationX(theta), 'RZ': qc.RotationZ(theta), 'CNOT': qc.CNOT(),
+                  'CZ': qc.ControlledU(qc.PauliZ())}[name], list(qs))
+    passes = c.schedule(dtype, fuse=True, max_ops=16)
+    order = [i for p in passes for i in p]
+    assert sorted(order) == list(range(len(c)))
+    assert all(len(p) <= 16 for p in passes)
+    assert len(passes) < len(c) / 2                      # fusion actually happens
+    vec = rand_state_vec(rng, n)
+    want = _run_oracle(c, range(len(c)), vec)
+    got = _run_oracle(c, order, vec)
+    assert np.max(np.abs(got - want)) < 1e-12
+    # every pass fits a tile: dense targets above the low bits number at most tile - low
+    low, tile = (10, 13) if dtype == np.complex64 else (9, 12)
+    for p in passes:
+        if len(p) == 1:
+            continue
+        nd = 0
+        for i in p:
+            nd |= c.gates[i].nd_mask
+        assert bin(nd >> low).count('1') <= tile - low
+
+
+def test_headline_circuit_fuses_well():
+    c = _layered(30, 40)
+    assert len(c) == 1780
+    passes = c.schedule(np.complex64, fuse=True, max_ops=24)
+    assert sorted(i for p in passes for i in p) == list(range(1780))
+    assert len(passes) < 500
+    unfused = c.schedule(np.complex64, fuse=False)
+    assert len(unfused) == 1780
