@@ -4,6 +4,7 @@ Tolerances (BASELINE.json north_star): complex128 1e-12, complex64 1e-5, relativ
 amplitude; measurement outcomes identical for identical uniform draws."""
 import copy
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -17,7 +18,8 @@ from tests.util import TOL, oracle_apply, rand_state_vec, rand_unitary, rel_err
 pytestmark = pytest.mark.gpu
 
 DTYPES = [np.complex128, np.complex64]
-MODES = [0, 1]   # 0 = cooperative staging, 1 = TMA bulk-copy pipeline
+# 0 = cooperative staging, 1 = TMA bulk-copy pipeline (QCS_TEST_MODES narrows the set, e.g. "0")
+MODES = [int(m) for m in os.environ.get('QCS_TEST_MODES', '0,1').split(',')]
 
 
 @pytest.fixture(autouse=True)
