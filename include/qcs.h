@@ -69,8 +69,8 @@ int64_t qcs_workspace_bytes(void);
  * tile_bits : at most tile_bits bits (low ones included) can be touched by dense ops of one pass */
 int qcs_tile_limits(int dtype, int *low_bits, int *tile_bits);
 
-/* Tuning hook (not a replacement for any reference call): 0 = cooperative load/store staging,
- * 1 = TMA bulk-copy pipeline.  Also settable with the QCS_TILE_MODE=plain|bulk environment variable. */
+/* Tuning hook (not a replacement for any reference call): 0 = cp.async ring with padded shared-memory
+ * layout (default), 1 = TMA bulk-copy ring.  Also settable with QCS_TILE_MODE=pipe|bulk. */
 int qcs_set_tile_mode(int mode);
 
 /* K1/K3: Operator._apply on a State (operators.py:225-278): dst = M applied to src on bitpos,

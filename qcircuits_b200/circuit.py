@@ -73,7 +73,7 @@ class Circuit:
         L = min(low.value, n)
         hcap = max(0, min(tile.value - low.value, n - L))
         low_mask = (1 << L) - 1
-        pool_cap = 20480 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
+        pool_cap = 12288 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
         max_ops = min(max_ops, _lib.QCS_MAX_OPS)
         gates = self.gates
         remaining = list(range(len(gates)))

@@ -33,11 +33,17 @@ const DeviceInfo &device_info() {
     return info[dev];
 }
 
+int tune_int(const char *name, int fallback) {
+    const char *e = std::getenv(name);
+    if (!e || !*e) return fallback;
+    return std::atoi(e);
+}
+
 static int g_tile_mode = -1;
 int tile_mode() {
     if (g_tile_mode < 0) {
         const char *e = std::getenv("QCS_TILE_MODE");
-        g_tile_mode = (e && std::strcmp(e, "plain") == 0)  ? TILE_MODE_PLAIN
+        g_tile_mode = (e && std::strcmp(e, "pipe") == 0)   ? TILE_MODE_PIPE
                       : (e && std::strcmp(e, "bulk") == 0) ? TILE_MODE_BULK
                                                            : TILE_MODE_DEFAULT;
     }
@@ -62,7 +68,7 @@ const char *qcs_last_error(void) { return g_err; }
 int64_t qcs_workspace_bytes(void) { return WS_BYTES; }
 
 int qcs_set_tile_mode(int mode) {
-    if (mode != TILE_MODE_PLAIN && mode != TILE_MODE_BULK) return set_error(QCS_ERR_ARG, "tile mode must be 0 or 1");
+    if (mode != TILE_MODE_PIPE && mode != TILE_MODE_BULK) return set_error(QCS_ERR_ARG, "tile mode must be 0 or 1");
     g_tile_mode = mode;
     return QCS_OK;
 }

@@ -10,32 +10,54 @@ namespace qcs {
 // ---- tile engine geometry ----------------------------------------------------------------------
 constexpr int TILE_LOW_BITS_C64 = 10;    // 2^10 complex64  = 8 KB contiguous chunk
 constexpr int TILE_LOW_BITS_C128 = 9;    // 2^9  complex128 = 8 KB contiguous chunk
+constexpr int TILE_MIN_BITS_C64 = 12;    // tiles are padded with free bits up to 32 KB (bytes in flight)
+constexpr int TILE_MIN_BITS_C128 = 11;
 constexpr int TILE_MAX_BITS_C64 = 13;    // 64 KB tile
 constexpr int TILE_MAX_BITS_C128 = 12;   // 64 KB tile
 constexpr int TILE_MAX_H = 8;
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_THREADS_BULK = 512;
 constexpr int TILE_MAX_STAGES = 4;
-constexpr size_t TILE_SMEM_BUDGET = 200 * 1024;   // dynamic shared memory per SM we plan against
-constexpr size_t TILE_STAGE_BUDGET = 96 * 1024;   // per CTA, pipelined variant
-constexpr int TILE_MODE_PLAIN = 0;
-constexpr int TILE_MODE_BULK = 1;
-constexpr int TILE_MODE_DEFAULT = TILE_MODE_PLAIN;
-constexpr int TILEOP_SCALE = 1;
+constexpr size_t TILE_SMEM_BUDGET = 220 * 1024;   // dynamic shared memory per SM we plan against
+constexpr int TILE_MODE_PIPE = 0;        // cp.async multi-stage pipeline, padded shared-memory layout
+constexpr int TILE_MODE_BULK = 1;        // TMA bulk-copy pipeline (cp.async.bulk + mbarrier), linear layout
+constexpr int TILE_MODE_DEFAULT = TILE_MODE_PIPE;
 
+constexpr int REG_BITS_C64 = 4;          // amplitudes a thread holds in registers per sweep: 2^4 float2
+constexpr int REG_BITS_C128 = 3;         //                                                   2^3 double2
+constexpr int REG_BITS_MAX = 4;
+
+// ops that cannot run in registers (dense on >= 2 targets) go through shared memory one at a time
 struct TileOp {
     int32_t kind, k, mat, flags;
-    int8_t lpos[QCS_MAX_OP_QUBITS];  // tile-local bit of operator qubit j (MSB-first); -1 = outside the tile (diag only)
+    int8_t lpos[QCS_MAX_OP_QUBITS];  // tile-local bit of operator qubit j (MSB-first)
     int8_t gpos[QCS_MAX_OP_QUBITS];  // flat bit of operator qubit j
     uint32_t ctrl_local;             // control bits inside the tile (tile-local mask)
     uint32_t pad;
     uint64_t ctrl_outer;             // control bits outside the tile (flat-index mask)
 };
 
-template <int NOPS, int MATBYTES>
+// register-level ops of a sweep
+constexpr int REGOP_U1 = 0;      // 2x2 matrix on register bit j
+constexpr int REGOP_PHASE = 1;   // multiply the amplitudes whose index matches (care, val) by one complex number
+constexpr int U1_GENERAL = 0, U1_REAL = 1, U1_RXLIKE = 2, U1_ANTIDIAG = 3;
+struct RegOp {
+    uint8_t code, j, form, reg_care, reg_val, pad0, pad1, pad2;   // reg_*: masks over the sweep's register bits
+    uint32_t base_care, base_val;                                 // tile-local index bits that are not register bits
+    uint64_t outer_care, outer_val;                               // flat-index bits outside the tile
+    int32_t mat, pad3;                                            // pool offset (U1: 4 entries row-major, PHASE: 1)
+};
+constexpr int SWEEP_REG = 0, SWEEP_GENERIC = 1;
+struct Sweep {
+    int32_t kind, first, count, nreg;
+    int8_t rpos[REG_BITS_MAX];       // tile-local positions of the register bits, ascending
+    int32_t pad;
+};
+
+template <int NSW, int NREG, int NGEN, int MATBYTES>
 struct TileProgram {
-    static constexpr int MAXOPS = NOPS;
-    int32_t n, L, H, nops, stages, mat_bytes;
+    static constexpr int MAX_SWEEPS = NSW, MAX_REGOPS = NREG, MAX_GENERIC = NGEN, MAT_BYTES = MATBYTES;
+    int32_t n, L, H, nsweeps, nregops, ngen, stages, mat_bytes;
     int32_t hbits[TILE_MAX_H];
     uint64_t ntiles;
     const void *src;
@@ -43,16 +65,19 @@ struct TileProgram {
     const double *norm_in;
     double *norm_out;
     void *ws;
-    TileOp ops[NOPS];
+    Sweep sweeps[NSW];
+    RegOp regops[NREG];
+    TileOp gen[NGEN];
     alignas(16) unsigned char mats[MATBYTES];
 };
-using SmallProg = TileProgram<4, 4096 + 64>;
-using LargeProg = TileProgram<QCS_MAX_OPS + 2, 20480>;
+using SmallProg = TileProgram<4, 34, 2, 4096 + 64>;
+using LargeProg = TileProgram<72, 200, QCS_MAX_OPS, 12288>;
 static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes");
 
 struct DeviceInfo { int sms; size_t smem_per_sm; };
 const DeviceInfo &device_info();
 int tile_mode();
+int tune_int(const char *name, int fallback);
 int set_error(int code, const char *msg);
 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,

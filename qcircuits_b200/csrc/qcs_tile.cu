@@ -6,23 +6,46 @@
 // Data layout in HBM: flat array of 2^n interleaved complex amplitudes (float2 / double2).
 // A pass picks a set of "tile bits": the low L flat bits (a contiguous 2^L-amplitude chunk, 8 KB)
 // plus H arbitrary high bits.  One tile = 2^H chunks = every amplitude that differs only in tile
-// bits, so any gate whose targets are tile bits is local to a tile.  A CTA stages a tile in shared
-// memory (coalesced 16-byte loads, or TMA bulk copies in the pipelined variant), applies the whole
-// op list in shared memory / registers, accumulates the squared norm, and streams the tile out:
-// each amplitude is read from HBM once and written once per pass however many gates are fused.
-// Diagonal ops and control bits may address ANY bit (their outer bits are tile-uniform).
+// bits, so any gate whose targets are tile bits is local to a tile.  A CTA streams tiles through a
+// multi-stage shared-memory ring (cp.async, or TMA bulk copies in the alternative variant), and for
+// each tile runs the op list as a few *register sweeps*: a thread pulls the 2^r amplitudes spanned by
+// r tile bits into registers, applies every gate of the sweep that acts on those bits (2x2 butterflies,
+// controlled or not, and phase multiplications on any bits) and writes them back.  The squared norm is
+// accumulated and the lazy 1/sqrt(norm) folded in while the tile streams out: each amplitude is read
+// from HBM once and written once per pass however many gates are fused.
 #include "qcs_common.cuh"
 #include "qcs_internal.h"
 
 namespace qcs {
 
 // ------------------------------------------------------------------------------------------------
-// op application on a tile held in shared memory
+// shared-memory layouts (indices in units of one amplitude / one 16-byte vector)
 // ------------------------------------------------------------------------------------------------
-template <typename R, int K>
+// Padded: one 16-byte pad after every 128-byte row.  A thread that owns 2^r consecutive amplitudes
+// (register bits = low bits) then strides 144 bytes between lanes instead of 128: conflict-free for
+// 128-bit accesses.  Both maps are additive over disjoint bit sets (no carries), which the sweep uses.
+template <typename C> struct PaddedLayout {
+    static constexpr int ROW = 128 / sizeof(C);                 // amplitudes per row
+    static constexpr int PADA = 16 / sizeof(C);                 // pad, in amplitudes
+    static __host__ __device__ __forceinline__ uint32_t amp(uint32_t i) { return i + (i / ROW) * PADA; }
+    static __host__ __device__ __forceinline__ uint32_t vec(uint32_t v) { return v + (v >> 3); }
+    static __host__ __device__ __forceinline__ size_t bytes(int m) {
+        const size_t raw = sizeof(C) << m;
+        return raw + ((raw + 127) / 128) * 16;
+    }
+};
+template <typename C> struct LinearLayout {
+    static __host__ __device__ __forceinline__ uint32_t amp(uint32_t i) { return i; }
+    static __host__ __device__ __forceinline__ uint32_t vec(uint32_t v) { return v; }
+    static __host__ __device__ __forceinline__ size_t bytes(int m) { return sizeof(C) << m; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// generic ops in shared memory (dense on 2..4 targets)
+// ------------------------------------------------------------------------------------------------
+template <typename R, int K, typename Layout>
 __device__ __forceinline__ void apply_dense(typename CxT<R>::T *tile, int m, const TileOp &op,
-                                            const typename CxT<R>::T *__restrict__ M, R scale,
-                                            int tid, int nt) {
+                                            const typename CxT<R>::T *__restrict__ M, int tid, int nt) {
     using C = typename CxT<R>::T;
     constexpr int D = 1 << K;
     int sp[K];  // target positions, ascending
@@ -40,124 +63,231 @@ __device__ __forceinline__ void apply_dense(typename CxT<R>::T *tile, int m, con
 #pragma unroll
         for (int j = 0; j < K; ++j)
             if ((x >> (K - 1 - j)) & 1) o |= 1u << op.lpos[j];
-        off[x] = o;
+        off[x] = Layout::amp(o);
     }
-    const bool scaled = (op.flags & TILEOP_SCALE) != 0;
     const uint32_t ctrl = op.ctrl_local;
     const uint32_t ngroups = 1u << (m - K);
-    // small matrices live in registers for the whole sweep; larger ones are broadcast-read from smem
-    constexpr bool MREG = (K == 1);
-    constexpr int DR = MREG ? D * D : 1;
-    C Mr[DR];
-    if (MREG) {
-#pragma unroll
-        for (int e = 0; e < DR; ++e) {
-            Mr[e] = M[e];
-            if (scaled) { Mr[e].x *= scale; Mr[e].y *= scale; }
-        }
-    }
     for (uint32_t g = tid; g < ngroups; g += nt) {
         uint32_t base = g;
 #pragma unroll
         for (int j = 0; j < K; ++j) base = insert_zero32(base, sp[j]);
         if ((base & ctrl) != ctrl) continue;
+        const uint32_t pb = Layout::amp(base);
         C a[D];
 #pragma unroll
-        for (int x = 0; x < D; ++x) a[x] = tile[base + off[x]];
+        for (int x = 0; x < D; ++x) a[x] = tile[pb + off[x]];
 #pragma unroll
         for (int y = 0; y < D; ++y) {
             C acc = cx<R>(R(0), R(0));
-            if (MREG) {
 #pragma unroll
-                for (int x = 0; x < D; ++x) cfma(acc, Mr[(y * D + x) % DR], a[x]);
-            } else {
-#pragma unroll
-                for (int x = 0; x < D; ++x) cfma(acc, M[y * D + x], a[x]);
-                if (scaled) { acc.x *= scale; acc.y *= scale; }
-            }
-            tile[base + off[y]] = acc;
+            for (int x = 0; x < D; ++x) cfma(acc, M[y * D + x], a[x]);
+            tile[pb + off[y]] = acc;
         }
     }
 }
 
-// A run of consecutive diagonal ops [i0, i1) is applied in one sweep over the tile.
-template <typename R>
-__device__ __forceinline__ void apply_diag_run(typename CxT<R>::T *tile, int m, const TileOp *ops,
-                                               int i0, int i1, const typename CxT<R>::T *__restrict__ pool,
-                                               uint64_t tile_base, R scale, int tid, int nt) {
+template <typename R, typename Layout>
+__device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, const TileOp &op,
+                                              const typename CxT<R>::T *pool, uint64_t tile_base, int tid, int nt) {
     using C = typename CxT<R>::T;
-    const uint32_t namp = 1u << m;
-    for (uint32_t l = tid; l < namp; l += nt) {
-        C a = tile[l];
-        for (int i = i0; i < i1; ++i) {
-            const TileOp &op = ops[i];
-            if ((l & op.ctrl_local) != op.ctrl_local) continue;
-            uint32_t x = 0;
-            for (int j = 0; j < op.k; ++j) {
-                const int lp = op.lpos[j];
-                const uint32_t bit = lp >= 0 ? ((l >> lp) & 1u) : (uint32_t)((tile_base >> op.gpos[j]) & 1ull);
-                x = (x << 1) | bit;
-            }
-            a = cmul(pool[op.mat + x], a);
-            if (op.flags & TILEOP_SCALE) { a.x *= scale; a.y *= scale; }
-        }
-        tile[l] = a;
+    if ((tile_base & op.ctrl_outer) != op.ctrl_outer) return;   // tile-uniform control
+    const C *M = pool + op.mat;
+    switch (op.k) {
+        case 1: apply_dense<R, 1, Layout>(tile, m, op, M, tid, nt); break;
+        case 2: apply_dense<R, 2, Layout>(tile, m, op, M, tid, nt); break;
+        case 3: apply_dense<R, 3, Layout>(tile, m, op, M, tid, nt); break;
+        default: apply_dense<R, 4, Layout>(tile, m, op, M, tid, nt); break;
     }
 }
 
-template <typename R, int KMAX>
-__device__ __forceinline__ void apply_ops(typename CxT<R>::T *tile, const TileOp *ops, int nops,
-                                          const typename CxT<R>::T *pool, int m, uint64_t tile_base,
-                                          R scale, int tid, int nt) {
+// ------------------------------------------------------------------------------------------------
+// register sweeps
+// ------------------------------------------------------------------------------------------------
+template <typename R, int NX, int J>
+__device__ __forceinline__ void u1_butterfly(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
+                                             int form, uint32_t rc, uint32_t rv, bool tp) {
     using C = typename CxT<R>::T;
-    int i = 0;
-    while (i < nops) {
-        const TileOp &op = ops[i];
-        if ((tile_base & op.ctrl_outer) != op.ctrl_outer) { ++i; continue; }  // tile-uniform
-        if (op.kind == QCS_OP_DIAG) {
-            int j = i + 1;
-            while (j < nops && ops[j].kind == QCS_OP_DIAG &&
-                   (tile_base & ops[j].ctrl_outer) == ops[j].ctrl_outer) ++j;
-            apply_diag_run<R>(tile, m, ops, i, j, pool, tile_base, scale, tid, nt);
-            i = j;
-        } else {
-            const C *M = pool + op.mat;
-            if (KMAX <= 2) {
-                if (op.k == 1) apply_dense<R, 1>(tile, m, op, M, scale, tid, nt);
-                else apply_dense<R, 2>(tile, m, op, M, scale, tid, nt);
+    constexpr uint32_t BIT = 1u << J;
+    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+    for (uint32_t x0 = 0; x0 < NX; ++x0) {
+        if (x0 & BIT) continue;
+        const uint32_t x1 = x0 | BIT;
+        if (((x0 & rc) == rv) && tp) {        // first part uniform across the CTA, second per thread
+            const C t0 = a[x0], t1 = a[x1];
+            C r0, r1;
+            if (form == U1_REAL) {
+                r0.x = fma(m00.x, t0.x, m01.x * t1.x); r0.y = fma(m00.x, t0.y, m01.x * t1.y);
+                r1.x = fma(m10.x, t0.x, m11.x * t1.x); r1.y = fma(m10.x, t0.y, m11.x * t1.y);
+            } else if (form == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
+                r0.x = fma(m00.x, t0.x, -m01.y * t1.y); r0.y = fma(m00.x, t0.y, m01.y * t1.x);
+                r1.x = fma(m11.x, t1.x, -m10.y * t0.y); r1.y = fma(m11.x, t1.y, m10.y * t0.x);
+            } else if (form == U1_ANTIDIAG) {
+                r0 = cmul(m01, t1);
+                r1 = cmul(m10, t0);
             } else {
-                switch (op.k) {
-                    case 1: apply_dense<R, 1>(tile, m, op, M, scale, tid, nt); break;
-                    case 2: apply_dense<R, 2>(tile, m, op, M, scale, tid, nt); break;
-                    case 3: apply_dense<R, 3>(tile, m, op, M, scale, tid, nt); break;
-                    default: apply_dense<R, 4>(tile, m, op, M, scale, tid, nt); break;
+                r0 = cmul(m00, t0); cfma(r0, m01, t1);
+                r1 = cmul(m10, t0); cfma(r1, m11, t1);
+            }
+            a[x0] = r0; a[x1] = r1;
+        }
+    }
+}
+
+template <typename R, int RB, typename Layout>
+__device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const Sweep &sw, const RegOp *rops,
+                                          const typename CxT<R>::T *pool, uint64_t tile_base, int tid, int nt) {
+    using C = typename CxT<R>::T;
+    constexpr int NX = 1 << RB;
+    const int nreg = sw.nreg;
+    const uint32_t nx_used = 1u << nreg;
+    uint32_t ps[RB];      // shared-memory stride of each register bit (layout maps are additive)
+#pragma unroll
+    for (int j = 0; j < RB; ++j) ps[j] = j < nreg ? Layout::amp(1u << sw.rpos[j]) : 0u;
+    const bool pair_vec = (sizeof(C) == 8) && nreg >= 1 && sw.rpos[0] == 0;   // complex64 pairs as one 128-bit access
+    const uint32_t ngroups = 1u << (m - nreg);
+    for (uint32_t g = tid; g < ngroups; g += nt) {
+        uint32_t base = g;
+        for (int j = 0; j < nreg; ++j) base = insert_zero32(base, sw.rpos[j]);
+        const uint32_t pb = Layout::amp(base);
+        uint32_t addr[NX];
+#pragma unroll
+        for (uint32_t x = 0; x < NX; ++x) {
+            uint32_t o = pb;
+#pragma unroll
+            for (int j = 0; j < RB; ++j)
+                if (x & (1u << j)) o += ps[j];
+            addr[x] = o;
+        }
+        C a[NX];
+        if (pair_vec) {
+#pragma unroll
+            for (uint32_t x = 0; x < NX; x += 2) {
+                if (x < nx_used) {
+                    const float4 v = *reinterpret_cast<const float4 *>(&tile[addr[x]]);
+                    a[x].x = v.x; a[x].y = v.y; a[x + 1].x = v.z; a[x + 1].y = v.w;
                 }
             }
-            ++i;
+        } else {
+#pragma unroll
+            for (uint32_t x = 0; x < NX; ++x)
+                if (x < nx_used) a[x] = tile[addr[x]];
         }
-        __syncthreads();
+        C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
+        bool have_ph = false;
+        for (int o = 0; o < sw.count; ++o) {
+            const RegOp &op = rops[sw.first + o];
+            if ((tile_base & op.outer_care) != op.outer_val) continue;           // tile-uniform
+            const bool tp = (base & op.base_care) == op.base_val;                // per thread
+            const uint32_t rc = op.reg_care, rv = op.reg_val;
+            if (op.code == REGOP_PHASE) {
+                const C d = pool[op.mat];
+                if (rc == 0) {
+                    if (tp) { ph = cmul(d, ph); have_ph = true; }
+                } else {
+#pragma unroll
+                    for (uint32_t x = 0; x < NX; ++x)
+                        if (((x & rc) == rv) && tp) a[x] = cmul(d, a[x]);
+                }
+            } else {
+                const C *M = pool + op.mat;
+                const int form = op.form;
+                switch (op.j) {
+                    case 0: u1_butterfly<R, NX, 0>(a, M, form, rc, rv, tp); break;
+                    case 1: if (RB > 1) u1_butterfly<R, NX, (RB > 1 ? 1 : 0)>(a, M, form, rc, rv, tp); break;
+                    case 2: if (RB > 2) u1_butterfly<R, NX, (RB > 2 ? 2 : 0)>(a, M, form, rc, rv, tp); break;
+                    default: if (RB > 3) u1_butterfly<R, NX, (RB > 3 ? 3 : 0)>(a, M, form, rc, rv, tp); break;
+                }
+            }
+        }
+        if (have_ph) {
+#pragma unroll
+            for (uint32_t x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
+        }
+        if (pair_vec) {
+#pragma unroll
+            for (uint32_t x = 0; x < NX; x += 2) {
+                if (x < nx_used) {
+                    float4 v;
+                    v.x = a[x].x; v.y = a[x].y; v.z = a[x + 1].x; v.w = a[x + 1].y;
+                    *reinterpret_cast<float4 *>(&tile[addr[x]]) = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (uint32_t x = 0; x < NX; ++x)
+                if (x < nx_used) tile[addr[x]] = a[x];
+        }
     }
 }
 
+// The program as staged in shared memory.
+struct ProgView {
+    const Sweep *sweeps;
+    const RegOp *regops;
+    const TileOp *gen;
+    const void *pool;
+    int nsweeps;
+};
+
+__host__ __device__ __forceinline__ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 __host__ __device__ __forceinline__ uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
 
-// copy the op list and matrix pool from kernel-parameter space into shared memory (once per CTA)
-template <typename Prog>
-__device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Prog &P, int tid, int nt) {
-    const uint32_t ops_words = (uint32_t)(P.nops * sizeof(TileOp) / 4);
-    const uint32_t ops_bytes = align128(ops_words * 4);
-    const uint32_t *po = reinterpret_cast<const uint32_t *>(P.ops);
-    uint32_t *so = reinterpret_cast<uint32_t *>(smem);
-    for (uint32_t i = tid; i < ops_words; i += nt) so[i] = po[i];
-    const uint32_t mat_words = (uint32_t)P.mat_bytes / 4;
-    const uint32_t *pm = reinterpret_cast<const uint32_t *>(P.mats);
-    uint32_t *sm = reinterpret_cast<uint32_t *>(smem + ops_bytes);
-    for (uint32_t i = tid; i < mat_words; i += nt) sm[i] = pm[i];
-    return ops_bytes;
-}
 template <typename Prog>
 static uint32_t program_smem_bytes(const Prog &P) {
-    return align128((uint32_t)(P.nops * sizeof(TileOp))) + align128((uint32_t)P.mat_bytes);
+    return align128(align16(P.nsweeps * (uint32_t)sizeof(Sweep)) + align16(P.nregops * (uint32_t)sizeof(RegOp)) +
+                    align16(P.ngen * (uint32_t)sizeof(TileOp)) + align16((uint32_t)P.mat_bytes) +
+                    (uint32_t)sizeof(uint64_t) * (1u << P.H));
+}
+
+__device__ __forceinline__ void copy_words(void *dst, const void *src, uint32_t bytes, int tid, int nt) {
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t i = tid; i < bytes / 4; i += nt) d[i] = s[i];
+}
+
+// copy the program from kernel-parameter space into shared memory (once per CTA); returns its size
+template <typename Prog>
+__device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Prog &P, ProgView &pv,
+                                                  const uint64_t *&chunk_off, int tid, int nt) {
+    uint32_t o = 0;
+    pv.sweeps = reinterpret_cast<const Sweep *>(smem + o);
+    copy_words(smem + o, P.sweeps, P.nsweeps * (uint32_t)sizeof(Sweep), tid, nt);
+    o += align16(P.nsweeps * (uint32_t)sizeof(Sweep));
+    pv.regops = reinterpret_cast<const RegOp *>(smem + o);
+    copy_words(smem + o, P.regops, P.nregops * (uint32_t)sizeof(RegOp), tid, nt);
+    o += align16(P.nregops * (uint32_t)sizeof(RegOp));
+    pv.gen = reinterpret_cast<const TileOp *>(smem + o);
+    copy_words(smem + o, P.gen, P.ngen * (uint32_t)sizeof(TileOp), tid, nt);
+    o += align16(P.ngen * (uint32_t)sizeof(TileOp));
+    pv.pool = smem + o;
+    copy_words(smem + o, P.mats, (uint32_t)P.mat_bytes, tid, nt);
+    o += align16((uint32_t)P.mat_bytes);
+    uint64_t *co = reinterpret_cast<uint64_t *>(smem + o);
+    for (uint32_t c = tid; c < (1u << P.H); c += nt) {
+        uint64_t off = 0;
+        for (int j = 0; j < P.H; ++j)
+            if ((c >> j) & 1u) off |= 1ull << P.hbits[j];
+        co[c] = off;
+    }
+    chunk_off = co;
+    o += (uint32_t)sizeof(uint64_t) * (1u << P.H);
+    pv.nsweeps = P.nsweeps;
+    return align128(o);
+}
+
+template <typename R, typename Layout>
+__device__ __forceinline__ void run_program(typename CxT<R>::T *tile, const ProgView &pv, int m, uint64_t tile_base,
+                                            int tid, int nt) {
+    using C = typename CxT<R>::T;
+    constexpr int RB = sizeof(C) == 8 ? REG_BITS_C64 : REG_BITS_C128;
+    const C *pool = reinterpret_cast<const C *>(pv.pool);
+    for (int s = 0; s < pv.nsweeps; ++s) {
+        const Sweep &sw = pv.sweeps[s];
+        if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout>(tile, m, sw, pv.regops, pool, tile_base, tid, nt);
+        else apply_generic<R, Layout>(tile, m, pv.gen[sw.first], pool, tile_base, tid, nt);
+        __syncthreads();
+    }
 }
 
 template <typename Prog>
@@ -165,13 +295,6 @@ __device__ __forceinline__ uint64_t tile_base_of(uint64_t t, const Prog &P) {
     uint64_t x = t;
     for (int j = 0; j < P.H; ++j) x = insert_zero(x, P.hbits[j] - P.L);
     return x << P.L;
-}
-template <typename Prog>
-__device__ __forceinline__ uint64_t chunk_offset(uint32_t c, const Prog &P) {
-    uint64_t o = 0;
-    for (int j = 0; j < P.H; ++j)
-        if ((c >> j) & 1u) o |= 1ull << P.hbits[j];
-    return o;
 }
 
 template <typename R> __device__ __forceinline__ double vec_abs2(const uint4 v);
@@ -184,59 +307,101 @@ template <> __device__ __forceinline__ double vec_abs2<double>(const uint4 v) {
     const double a = __hiloint2double(v.y, v.x), b = __hiloint2double(v.w, v.z);
     return a * a + b * b;
 }
+template <typename R> __device__ __forceinline__ uint4 vec_scale(const uint4 v, R s);
+template <> __device__ __forceinline__ uint4 vec_scale<float>(const uint4 v, float s) {
+    uint4 r;
+    r.x = __float_as_uint(__uint_as_float(v.x) * s); r.y = __float_as_uint(__uint_as_float(v.y) * s);
+    r.z = __float_as_uint(__uint_as_float(v.z) * s); r.w = __float_as_uint(__uint_as_float(v.w) * s);
+    return r;
+}
+template <> __device__ __forceinline__ uint4 vec_scale<double>(const uint4 v, double s) {
+    const double a = __hiloint2double(v.y, v.x) * s, b = __hiloint2double(v.w, v.z) * s;
+    uint4 r;
+    r.x = __double2loint(a); r.y = __double2hiint(a); r.z = __double2loint(b); r.w = __double2hiint(b);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------------------------------------
-// Variant 1: cooperative loads/stores, one tile per CTA iteration, several CTAs per SM
+// Variant 0: cp.async ring, padded layout, every warp both copies and computes
 // ------------------------------------------------------------------------------------------------
-template <typename R, typename Prog, int KMAX>
-__global__ void __launch_bounds__(TILE_THREADS, KMAX <= 2 ? 4 : 2) tile_kernel(const __grid_constant__ Prog P) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {   // n = groups allowed to remain in flight
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+
+template <typename R, typename Prog>
+__global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid_constant__ Prog P) {
     using C = typename CxT<R>::T;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using Layout = PaddedLayout<C>;
+    extern __shared__ __align__(128) unsigned char smem_all[];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t ops_bytes = stage_program(smem_raw, P, tid, nt);
-    const TileOp *s_ops = reinterpret_cast<const TileOp *>(smem_raw);
-    const C *s_pool = reinterpret_cast<const C *>(smem_raw + ops_bytes);
-    unsigned char *tile_raw = smem_raw + ops_bytes + align128((uint32_t)P.mat_bytes);
-    C *tile = reinterpret_cast<C *>(tile_raw);
-    uint4 *tile_v = reinterpret_cast<uint4 *>(tile_raw);
+    ProgView pv;
+    const uint64_t *chunk_off;
+    const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, nt);
+    unsigned char *ring = smem_all + prog_bytes;
     const int m = P.L + P.H;
+    const int S = P.stages;
+    const uint32_t stage_bytes = (uint32_t)Layout::bytes(m);
     constexpr int VSHIFT = sizeof(C) == 8 ? 1 : 0;       // amplitudes per 16-byte vector = 1 << VSHIFT
     const uint32_t tile_vecs = (1u << m) >> VSHIFT;
     const int chunk_vec_bits = P.L - VSHIFT;             // log2(vectors per chunk)
+    const uint32_t chunk_vec_mask = (1u << chunk_vec_bits) - 1u;
+    const bool rescale = P.norm_in != nullptr;
     const R scale = (R)load_inv_norm(P.norm_in);
     const uint4 *src = reinterpret_cast<const uint4 *>(P.src);
     uint4 *dst = reinterpret_cast<uint4 *>(P.dst);
     double nacc[1] = {0.0};
+    const uint64_t my_tiles = (P.ntiles > blockIdx.x) ? (P.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    __syncthreads();   // program + chunk table visible
 
-    for (uint64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
-        const uint64_t base = tile_base_of(t, P);
-        // stage in
+    auto issue_load = [&](uint64_t it) {
+        const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
+        uint4 *stage = reinterpret_cast<uint4 *>(ring + (size_t)(it % S) * stage_bytes);
         for (uint32_t v = tid; v < tile_vecs; v += nt) {
-            const uint32_t c = v >> chunk_vec_bits;
-            const uint64_t g = ((base + chunk_offset(c, P)) >> VSHIFT) + (v & ((1u << chunk_vec_bits) - 1u));
-            tile_v[v] = src[g];
+            const uint64_t g = ((base + chunk_off[v >> chunk_vec_bits]) >> VSHIFT) + (v & chunk_vec_mask);
+            cp_async16(&stage[Layout::vec(v)], &src[g]);
         }
-        __syncthreads();
-        apply_ops<R, KMAX>(tile, s_ops, P.nops, s_pool, m, base, scale, tid, nt);
-        // stage out (+ squared norm)
+    };
+
+    for (int s = 0; s < S - 1; ++s) {
+        if ((uint64_t)s < my_tiles) issue_load(s);
+        cp_async_commit();
+    }
+    for (uint64_t it = 0; it < my_tiles; ++it) {
+        cp_async_wait_pending(S - 2);      // this thread's copies of tile `it` have landed
+        __syncthreads();                   // ... everyone's have, and stage (it-1)%S is drained
+        const uint64_t nxt = it + (uint64_t)(S - 1);
+        if (nxt < my_tiles) issue_load(nxt);
+        cp_async_commit();
+        const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
+        unsigned char *stage = ring + (size_t)(it % S) * stage_bytes;
+        run_program<R, Layout>(reinterpret_cast<C *>(stage), pv, m, base, tid, nt);
+        const uint4 *stage_v = reinterpret_cast<const uint4 *>(stage);
         for (uint32_t v = tid; v < tile_vecs; v += nt) {
-            const uint32_t c = v >> chunk_vec_bits;
-            const uint64_t g = ((base + chunk_offset(c, P)) >> VSHIFT) + (v & ((1u << chunk_vec_bits) - 1u));
-            const uint4 val = tile_v[v];
+            const uint64_t g = ((base + chunk_off[v >> chunk_vec_bits]) >> VSHIFT) + (v & chunk_vec_mask);
+            uint4 val = stage_v[Layout::vec(v)];
+            if (rescale) val = vec_scale<R>(val, scale);
             nacc[0] += vec_abs2<R>(val);
             dst[g] = val;
         }
-        __syncthreads();
     }
+    cp_async_wait_pending(0);
     if (P.norm_out) grid_sum_publish<1>(nacc, P.ws, P.norm_out);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Variant 2: TMA bulk-copy pipeline (cp.async.bulk + mbarrier), S stages per CTA
+// Variant 1: TMA bulk-copy ring (cp.async.bulk + mbarrier), linear layout
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -277,28 +442,28 @@ template <int N> __device__ __forceinline__ void bulk_wait_all() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename R, typename Prog, int KMAX>
-__global__ void __launch_bounds__(TILE_THREADS_BULK, KMAX <= 2 ? 2 : 1) tile_kernel_bulk(const __grid_constant__ Prog P) {
+template <typename R, typename Prog>
+__global__ void __launch_bounds__(TILE_THREADS_BULK, 1) tile_kernel_bulk(const __grid_constant__ Prog P) {
     using C = typename CxT<R>::T;
+    using Layout = LinearLayout<C>;
     extern __shared__ __align__(128) unsigned char smem_all[];
     __shared__ __align__(8) uint64_t full_bar[TILE_MAX_STAGES];
 
     const int tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t ops_bytes = stage_program(smem_all, P, tid, nt);
-    const TileOp *s_ops = reinterpret_cast<const TileOp *>(smem_all);
-    const C *s_pool = reinterpret_cast<const C *>(smem_all + ops_bytes);
-    unsigned char *smem_raw = smem_all + ops_bytes + align128((uint32_t)P.mat_bytes);
+    ProgView pv;
+    const uint64_t *chunk_off;
+    const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, nt);
+    unsigned char *ring = smem_all + prog_bytes;
     const int m = P.L + P.H;
     const int S = P.stages;
     const uint32_t tile_bytes = (uint32_t)((sizeof(C)) << m);
     const uint32_t chunk_bytes = (uint32_t)((sizeof(C)) << P.L);
     const uint32_t nchunks = 1u << P.H;
+    const bool rescale = P.norm_in != nullptr;
     const R scale = (R)load_inv_norm(P.norm_in);
     const unsigned char *src = reinterpret_cast<const unsigned char *>(P.src);
     unsigned char *dst = reinterpret_cast<unsigned char *>(P.dst);
     double nacc[1] = {0.0};
-
-    // tiles owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const uint64_t my_tiles = (P.ntiles > blockIdx.x) ? (P.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (tid == 0) {
@@ -310,35 +475,37 @@ __global__ void __launch_bounds__(TILE_THREADS_BULK, KMAX <= 2 ? 2 : 1) tile_ker
     auto issue_load = [&](uint64_t it) {
         const int st = (int)(it % S);
         const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
-        unsigned char *sdst = smem_raw + (size_t)st * tile_bytes;
+        unsigned char *sdst = ring + (size_t)st * tile_bytes;
         mbar_expect_tx(&full_bar[st], tile_bytes);
         for (uint32_t c = 0; c < nchunks; ++c)
-            bulk_g2s(sdst + (size_t)c * chunk_bytes, src + (base + chunk_offset(c, P)) * sizeof(C), chunk_bytes,
-                     &full_bar[st]);
+            bulk_g2s(sdst + (size_t)c * chunk_bytes, src + (base + chunk_off[c]) * sizeof(C), chunk_bytes, &full_bar[st]);
     };
 
     if (tid == 0) {
         const uint64_t pre = my_tiles < (uint64_t)(S - 1) ? my_tiles : (uint64_t)(S - 1);
         for (uint64_t it = 0; it < pre; ++it) issue_load(it);
     }
-
     for (uint64_t it = 0; it < my_tiles; ++it) {
         const int st = (int)(it % S);
         const uint32_t parity = (uint32_t)((it / S) & 1);
         const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
-        C *tile = reinterpret_cast<C *>(smem_raw + (size_t)st * tile_bytes);
+        C *tile = reinterpret_cast<C *>(ring + (size_t)st * tile_bytes);
         mbar_wait(&full_bar[st], parity);
-        apply_ops<R, KMAX>(tile, s_ops, P.nops, s_pool, m, base, scale, tid, nt);
-        if (P.norm_out) {
-            const uint4 *tv = reinterpret_cast<const uint4 *>(tile);
+        run_program<R, Layout>(tile, pv, m, base, tid, nt);
+        if (P.norm_out || rescale) {
+            uint4 *tv = reinterpret_cast<uint4 *>(tile);
             const uint32_t tile_vecs = tile_bytes >> 4;
-            for (uint32_t v = tid; v < tile_vecs; v += nt) nacc[0] += vec_abs2<R>(tv[v]);
+            for (uint32_t v = tid; v < tile_vecs; v += nt) {
+                uint4 val = tv[v];
+                if (rescale) { val = vec_scale<R>(val, scale); tv[v] = val; }
+                nacc[0] += vec_abs2<R>(val);
+            }
         }
         fence_proxy_async();   // generic-proxy writes of this stage -> visible to the bulk store
         __syncthreads();
         if (tid == 0) {
             for (uint32_t c = 0; c < nchunks; ++c)
-                bulk_s2g(dst + (base + chunk_offset(c, P)) * sizeof(C),
+                bulk_s2g(dst + (base + chunk_off[c]) * sizeof(C),
                          reinterpret_cast<unsigned char *>(tile) + (size_t)c * chunk_bytes, chunk_bytes);
             bulk_commit();
             const uint64_t nxt = it + (uint64_t)(S - 1);
@@ -353,50 +520,72 @@ __global__ void __launch_bounds__(TILE_THREADS_BULK, KMAX <= 2 ? 2 : 1) tile_ker
 }
 
 // ------------------------------------------------------------------------------------------------
-// host side
+// host side: geometry, sweep planning, launch
 // ------------------------------------------------------------------------------------------------
-template <typename R, typename Prog, int KMAX>
-static int launch_tile(const Prog &P, const DeviceInfo &dev, int mode, cudaStream_t stream) {
+template <typename R, typename Prog>
+static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t stream) {
     using C = typename CxT<R>::T;
     const int m = P.L + P.H;
-    const size_t tile_bytes = sizeof(C) << m;
-    if (mode == TILE_MODE_BULK && tile_bytes >= 16 && (sizeof(C) << P.L) >= 16) {
-        auto kern = tile_kernel_bulk<R, Prog, KMAX>;
+    const size_t prog = program_smem_bytes(P);
+    if (mode == TILE_MODE_BULK && (sizeof(C) << P.L) >= 16) {
+        auto kern = tile_kernel_bulk<R, Prog>;
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BUDGET);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
             attr_done = true;
         }
-        const size_t smem = (size_t)P.stages * tile_bytes + program_smem_bytes(P);
-        int per_sm = (int)(TILE_SMEM_BUDGET / (smem + 1024));
-        if (per_sm > (KMAX <= 2 ? 2 : 1)) per_sm = (KMAX <= 2 ? 2 : 1);
-        if (per_sm < 1) per_sm = 1;
-        uint64_t grid = (uint64_t)dev.sms * per_sm;
+        const size_t tile_bytes = sizeof(C) << m;
+        int S = (int)((TILE_SMEM_BUDGET - prog - 1024) / tile_bytes);
+        S = S > TILE_MAX_STAGES ? TILE_MAX_STAGES : S;
+        S = tune_int("QCS_BULK_STAGES", S);
+        if (S < 2) S = 2;
+        if (S > TILE_MAX_STAGES) S = TILE_MAX_STAGES;
+        P.stages = S;
+        const size_t smem = (size_t)S * tile_bytes + prog;
+        if (smem > TILE_SMEM_BUDGET) return set_error(QCS_ERR_UNSUPPORTED, "tile does not fit shared memory");
+        uint64_t grid = (uint64_t)dev.sms;
         if (grid > P.ntiles) grid = P.ntiles;
-        if (grid > MAX_GRID) grid = MAX_GRID;
-        int threads = TILE_THREADS_BULK;
+        int threads = tune_int("QCS_BULK_THREADS", TILE_THREADS_BULK);
+        if (threads > TILE_THREADS_BULK) threads = TILE_THREADS_BULK;
         while (threads > 32 && (1u << m) < (unsigned)threads) threads >>= 1;
         kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     } else {
-        auto kern = tile_kernel<R, Prog, KMAX>;
+        auto kern = tile_kernel_pipe<R, Prog>;
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BUDGET);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
             attr_done = true;
         }
-        const size_t smem = (tile_bytes < 16 ? 16 : tile_bytes) + program_smem_bytes(P);
-        int per_sm = (int)(TILE_SMEM_BUDGET / (smem + 1024));
-        if (per_sm > (KMAX <= 2 ? 4 : 2)) per_sm = (KMAX <= 2 ? 4 : 2);
-        if (per_sm < 1) per_sm = 1;
-        uint64_t grid = (uint64_t)dev.sms * per_sm;
+        const size_t stage_bytes = PaddedLayout<C>::bytes(m);
+        int ctas = tune_int("QCS_PIPE_CTAS", 2);
+        if (ctas < 1) ctas = 1;
+        if (ctas > 2) ctas = 2;
+        int S = (int)((TILE_SMEM_BUDGET / ctas - prog - 1024) / stage_bytes);
+        while (S < 2 && ctas > 1) { --ctas; S = (int)((TILE_SMEM_BUDGET / ctas - prog - 1024) / stage_bytes); }
+        S = S > TILE_MAX_STAGES ? TILE_MAX_STAGES : S;
+        const int tuned = tune_int("QCS_PIPE_STAGES", S);
+        if (tuned < S) S = tuned;
+        if (S < 2) S = 2;
+        P.stages = S;
+        const size_t smem = (size_t)S * stage_bytes + prog;
+        if (smem > TILE_SMEM_BUDGET) return set_error(QCS_ERR_UNSUPPORTED, "tile does not fit shared memory");
+        uint64_t grid = (uint64_t)dev.sms * ctas;
         if (grid > P.ntiles) grid = P.ntiles;
         if (grid > MAX_GRID) grid = MAX_GRID;
         int threads = TILE_THREADS;
-        while (threads > 32 && (1u << m) < (unsigned)threads) threads >>= 1;
+        while (threads > 32 && (1u << m) < (unsigned)threads * 2u) threads >>= 1;
         kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     }
-    return cudaGetLastError() == cudaSuccess ? QCS_OK : QCS_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? QCS_OK : set_error(QCS_ERR_CUDA, "tile kernel launch failed");
 }
+
+namespace {
+struct HostOp {            // one entry of the caller's list, classified
+    int kind;              // 0 = U1 (one dense target), 1 = phases (any diagonal), 2 = generic dense
+    uint64_t nd_mask;      // flat bits acted on non-diagonally
+    uint64_t d_mask;       // flat bits acted on diagonally (controls, diagonal targets)
+};
+}  // namespace
 
 template <typename Prog>
 static int build_and_launch(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
@@ -407,7 +596,8 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     Prog &P = *Pp;
     struct Guard { Prog *p; ~Guard() { delete p; } } guard{Pp};
 
-    // ---- tile geometry: low L bits + the dense targets above them --------------------------------
+    // ---- validate + classify ------------------------------------------------------------------------
+    HostOp hop[QCS_MAX_OPS];
     uint64_t dense_mask = 0;
     for (int i = 0; i < nops; ++i) {
         const qcs_op &o = ops[i];
@@ -420,11 +610,24 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         }
         if (o.ctrl_mask & seen) return set_error(QCS_ERR_ARG, "control bit is also a target");
         if (n < 64 && (o.ctrl_mask >> n)) return set_error(QCS_ERR_ARG, "control bit out of range");
-        if (o.kind == QCS_OP_DENSE) dense_mask |= seen;
-        else if (o.kind != QCS_OP_DIAG) return set_error(QCS_ERR_ARG, "unknown op kind");
+        if (o.kind == QCS_OP_DENSE) {
+            dense_mask |= seen;
+            hop[i].kind = o.k == 1 ? 0 : 2;
+            hop[i].nd_mask = seen;
+            hop[i].d_mask = o.ctrl_mask;
+        } else if (o.kind == QCS_OP_DIAG) {
+            hop[i].kind = 1;
+            hop[i].nd_mask = 0;
+            hop[i].d_mask = seen | o.ctrl_mask;
+        } else {
+            return set_error(QCS_ERR_ARG, "unknown op kind");
+        }
     }
+
+    // ---- tile geometry: low L bits + the dense targets above them, padded to the minimum tile -------
     const int lpref = c64 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
     const int mmax = c64 ? TILE_MAX_BITS_C64 : TILE_MAX_BITS_C128;
+    const int mmin = c64 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
     int L = n < lpref ? n : lpref;
     int H = 0;
     for (;; --L) {
@@ -432,92 +635,190 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         if (L + H <= mmax) break;
         if (L <= vshift) return set_error(QCS_ERR_UNSUPPORTED, "fused ops touch too many high bits for one tile");
     }
+    uint64_t high_mask = (dense_mask >> L) << L;
+    for (int b = L; b < n && L + H < mmin; ++b)          // free bits: bigger tiles, more bytes in flight
+        if (!((high_mask >> b) & 1ull)) { high_mask |= 1ull << b; ++H; }
     if (H > TILE_MAX_H) return set_error(QCS_ERR_UNSUPPORTED, "too many high tile bits");
-    P.n = n; P.L = L; P.H = H; P.nops = nops;
+    P.n = n; P.L = L; P.H = H;
     {
         int h = 0;
         for (int b = L; b < n; ++b)
-            if ((dense_mask >> b) & 1ull) P.hbits[h++] = b;
+            if ((high_mask >> b) & 1ull) P.hbits[h++] = b;
     }
     const int m = L + H;
     P.ntiles = 1ull << (n - m);
     P.src = src; P.dst = dst; P.norm_in = norm_in; P.norm_out = norm_out; P.ws = ws;
-    uint64_t tile_mask = (L >= 64 ? ~0ull : ((1ull << L) - 1ull));
-    for (int h = 0; h < H; ++h) tile_mask |= 1ull << P.hbits[h];
+    const uint64_t tile_mask = ((1ull << L) - 1ull) | high_mask;
     auto local_of = [&](int b) -> int {
         if (b < L) return b;
         for (int h = 0; h < H; ++h) if (P.hbits[h] == b) return L + h;
         return -1;
     };
+    auto local_mask = [&](uint64_t flat) -> uint32_t {   // flat-index mask (inside the tile) -> tile-local mask
+        uint32_t r = 0;
+        for (int b = 0; b < n; ++b)
+            if ((flat >> b) & 1ull) r |= 1u << local_of(b);
+        return r;
+    };
 
-    // ---- ops + matrix pool ------------------------------------------------------------------------
+    // ---- matrix pool -----------------------------------------------------------------------------------
     const size_t csize = c64 ? 8 : 16;
     const size_t pool_cap = sizeof(P.mats) / csize;
     size_t used = 0;
-    bool scale_placed = (norm_in == nullptr);
-    for (int i = 0; i < nops; ++i) {
-        const qcs_op &o = ops[i];
-        TileOp &t = P.ops[i];
-        t.kind = o.kind; t.k = o.k; t.flags = 0;
-        const size_t entries = o.kind == QCS_OP_DENSE ? (size_t)1 << (2 * o.k) : (size_t)1 << o.k;
-        if (used + entries > pool_cap) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
-        t.mat = (int32_t)used;
+    auto push_entries = [&](const double *re_im, size_t entries) -> int {
+        if (used + entries > pool_cap) return -1;
+        const int at = (int)used;
         if (c64) {
             float *p = reinterpret_cast<float *>(P.mats) + 2 * used;
-            for (size_t e = 0; e < 2 * entries; ++e) p[e] = (float)o.matrix[e];
+            for (size_t e = 0; e < 2 * entries; ++e) p[e] = (float)re_im[e];
         } else {
             double *p = reinterpret_cast<double *>(P.mats) + 2 * used;
-            for (size_t e = 0; e < 2 * entries; ++e) p[e] = o.matrix[e];
+            for (size_t e = 0; e < 2 * entries; ++e) p[e] = re_im[e];
         }
         used += entries;
-        for (int j = 0; j < QCS_MAX_OP_QUBITS; ++j) { t.lpos[j] = -1; t.gpos[j] = 0; }
-        for (int j = 0; j < o.k; ++j) { t.lpos[j] = (int8_t)local_of(o.bitpos[j]); t.gpos[j] = (int8_t)o.bitpos[j]; }
-        t.ctrl_local = 0;
-        t.ctrl_outer = o.ctrl_mask & ~tile_mask;
-        for (int b = 0; b < n; ++b)
-            if (((o.ctrl_mask & tile_mask) >> b) & 1ull) t.ctrl_local |= 1u << local_of(b);
-        if (!scale_placed && o.ctrl_mask == 0) { t.flags |= TILEOP_SCALE; scale_placed = true; }
-    }
-    if (!scale_placed) {
-        // every op is controlled: append an uncontrolled identity diagonal that carries the scale
-        if (nops >= (int)(sizeof(P.ops) / sizeof(P.ops[0])) || used + 2 > pool_cap)
-            return set_error(QCS_ERR_UNSUPPORTED, "no room for the scale op");
-        TileOp &t = P.ops[nops];
-        t.kind = QCS_OP_DIAG; t.k = 1; t.flags = TILEOP_SCALE; t.mat = (int32_t)used;
-        for (int j = 0; j < QCS_MAX_OP_QUBITS; ++j) { t.lpos[j] = -1; t.gpos[j] = 0; }
-        t.lpos[0] = 0; t.gpos[0] = 0; t.ctrl_local = 0; t.ctrl_outer = 0;
-        if (c64) { float *p = reinterpret_cast<float *>(P.mats) + 2 * used; p[0] = 1; p[1] = 0; p[2] = 1; p[3] = 0; }
-        else { double *p = reinterpret_cast<double *>(P.mats) + 2 * used; p[0] = 1; p[1] = 0; p[2] = 1; p[3] = 0; }
-        P.nops = nops + 1;
-    }
+        return at;
+    };
 
-    P.mat_bytes = (int32_t)((used + 2) * csize);
-    if (P.mat_bytes > (int32_t)sizeof(P.mats)) P.mat_bytes = (int32_t)sizeof(P.mats);
+    // ---- sweeps: greedy, commuting ops may overtake ops that wait for a later sweep --------------------
+    const int rb = c64 ? REG_BITS_C64 : REG_BITS_C128;
+    const int nreg = rb < m ? rb : m;
+    int pending[QCS_MAX_OPS];
+    int npend = nops;
+    for (int i = 0; i < nops; ++i) pending[i] = i;
+    P.nsweeps = P.nregops = P.ngen = 0;
+    while (npend > 0) {
+        if (P.nsweeps >= Prog::MAX_SWEEPS) return set_error(QCS_ERR_UNSUPPORTED, "too many sweeps in one pass");
+        Sweep &sw = P.sweeps[P.nsweeps];
+        const int first = pending[0];
+        if (hop[first].kind == 2) {            // generic dense op: its own shared-memory sweep
+            const qcs_op &o = ops[first];
+            if (P.ngen >= Prog::MAX_GENERIC) return set_error(QCS_ERR_UNSUPPORTED, "too many generic ops");
+            TileOp &t = P.gen[P.ngen];
+            t.kind = o.kind; t.k = o.k; t.flags = 0;
+            const int at = push_entries(o.matrix, (size_t)1 << (2 * o.k));
+            if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
+            t.mat = at;
+            for (int j = 0; j < QCS_MAX_OP_QUBITS; ++j) { t.lpos[j] = -1; t.gpos[j] = 0; }
+            for (int j = 0; j < o.k; ++j) { t.lpos[j] = (int8_t)local_of(o.bitpos[j]); t.gpos[j] = (int8_t)o.bitpos[j]; }
+            t.ctrl_local = local_mask(o.ctrl_mask & tile_mask);
+            t.ctrl_outer = o.ctrl_mask & ~tile_mask;
+            sw.kind = SWEEP_GENERIC; sw.first = P.ngen; sw.count = 1; sw.nreg = 0;
+            ++P.ngen; ++P.nsweeps;
+            for (int i = 1; i < npend; ++i) pending[i - 1] = pending[i];
+            --npend;
+            continue;
+        }
+        // choose the ops of this register sweep
+        uint32_t S_local = 0;                  // tile-local mask of the register bits
+        int S_count = 0;
+        uint64_t blk_nd = 0, blk_d = 0;
+        int taken[QCS_MAX_OPS], ntaken = 0, rest[QCS_MAX_OPS], nrest = 0;
+        for (int i = 0; i < npend; ++i) {
+            const int idx = pending[i];
+            const HostOp &h = hop[idx];
+            bool can = h.kind != 2 && (h.nd_mask & (blk_nd | blk_d)) == 0 && (h.d_mask & blk_nd) == 0;
+            if (can && h.kind == 0) {
+                const uint32_t tbit = 1u << local_of(ops[idx].bitpos[0]);
+                if (!(S_local & tbit)) {
+                    if (S_count < nreg) { S_local |= tbit; ++S_count; }
+                    else can = false;
+                }
+            }
+            if (can) taken[ntaken++] = idx;
+            else { rest[nrest++] = idx; blk_nd |= h.nd_mask; blk_d |= h.d_mask; }
+        }
+        // complete the register set: first the aligned blocks that already hold a register bit, then from the top
+        for (int blk = 0; blk * nreg < m && S_count < nreg; ++blk) {
+            const uint32_t bm = ((1u << nreg) - 1u) << (blk * nreg);
+            if (!(S_local & bm)) continue;
+            for (int b = blk * nreg; b < (blk + 1) * nreg && b < m && S_count < nreg; ++b)
+                if (!(S_local & (1u << b))) { S_local |= 1u << b; ++S_count; }
+        }
+        for (int b = m - 1; b >= 0 && S_count < nreg; --b)
+            if (!(S_local & (1u << b))) { S_local |= 1u << b; ++S_count; }
+        sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg;
+        int8_t reg_index_of_local[32];
+        for (int b = 0, j = 0; b < 32; ++b) {
+            reg_index_of_local[b] = -1;
+            if ((S_local >> b) & 1u) {
+                if (j < REG_BITS_MAX) sw.rpos[j] = (int8_t)b;
+                reg_index_of_local[b] = (int8_t)j;
+                ++j;
+            }
+        }
+        auto split_masks = [&](uint64_t care, uint64_t val, RegOp &r) {
+            // flat-index (care, val) -> register / thread / tile parts
+            r.outer_care = care & ~tile_mask; r.outer_val = val & ~tile_mask;
+            r.reg_care = r.reg_val = 0; r.base_care = r.base_val = 0;
+            for (int b = 0; b < n; ++b) {
+                if (!(((care & tile_mask) >> b) & 1ull)) continue;
+                const int lb = local_of(b);
+                const bool one = (val >> b) & 1ull;
+                if (reg_index_of_local[lb] >= 0) {
+                    r.reg_care |= (uint8_t)(1u << reg_index_of_local[lb]);
+                    if (one) r.reg_val |= (uint8_t)(1u << reg_index_of_local[lb]);
+                } else {
+                    r.base_care |= 1u << lb;
+                    if (one) r.base_val |= 1u << lb;
+                }
+            }
+        };
+        for (int t = 0; t < ntaken; ++t) {
+            const qcs_op &o = ops[taken[t]];
+            if (hop[taken[t]].kind == 0) {
+                if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
+                RegOp &r = P.regops[P.nregops++];
+                r.code = REGOP_U1;
+                r.j = (uint8_t)reg_index_of_local[local_of(o.bitpos[0])];
+                const double *M = o.matrix;   // m00 m01 m10 m11 as (re, im)
+                const bool real = M[1] == 0 && M[3] == 0 && M[5] == 0 && M[7] == 0;
+                const bool rxl = M[1] == 0 && M[7] == 0 && M[2] == 0 && M[4] == 0;
+                const bool anti = M[0] == 0 && M[1] == 0 && M[6] == 0 && M[7] == 0;
+                r.form = (uint8_t)(real ? U1_REAL : anti ? U1_ANTIDIAG : rxl ? U1_RXLIKE : U1_GENERAL);
+                split_masks(o.ctrl_mask, o.ctrl_mask, r);
+                const int at = push_entries(M, 4);
+                if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
+                r.mat = at;
+                ++sw.count;
+            } else {
+                // diagonal on k bits: one phase op per basis pattern whose entry is not exactly 1
+                for (int x = 0; x < (1 << o.k); ++x) {
+                    const double re = o.matrix[2 * x], im = o.matrix[2 * x + 1];
+                    if (re == 1.0 && im == 0.0) continue;
+                    if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
+                    RegOp &r = P.regops[P.nregops++];
+                    r.code = REGOP_PHASE; r.j = 0; r.form = 0;
+                    uint64_t care = o.ctrl_mask, val = o.ctrl_mask;
+                    for (int j = 0; j < o.k; ++j) {
+                        care |= 1ull << o.bitpos[j];
+                        if ((x >> (o.k - 1 - j)) & 1) val |= 1ull << o.bitpos[j];
+                    }
+                    split_masks(care, val, r);
+                    const double d[2] = {re, im};
+                    const int at = push_entries(d, 1);
+                    if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
+                    r.mat = at;
+                    ++sw.count;
+                }
+            }
+        }
+        if (sw.count > 0) ++P.nsweeps;     // (a run of exact identities produces no work)
+        for (int i = 0; i < nrest; ++i) pending[i] = rest[i];
+        npend = nrest;
+    }
+    P.mat_bytes = (int32_t)(used * csize);
     const DeviceInfo &dev = device_info();
     const int mode = tile_mode();
-    const size_t tile_bytes = csize << m;
-    int S = (int)(TILE_STAGE_BUDGET / (tile_bytes ? tile_bytes : 1));
-    if (S > TILE_MAX_STAGES) S = TILE_MAX_STAGES;
-    if (S < 2) S = 2;
-    P.stages = S;
-    int kmax = 1;
-    for (int i = 0; i < nops; ++i)
-        if (ops[i].kind == QCS_OP_DENSE && ops[i].k > kmax) kmax = ops[i].k;
-    if (kmax <= 2)
-        return c64 ? launch_tile<float, Prog, 2>(P, dev, mode, stream) : launch_tile<double, Prog, 2>(P, dev, mode, stream);
-    return c64 ? launch_tile<float, Prog, 4>(P, dev, mode, stream) : launch_tile<double, Prog, 4>(P, dev, mode, stream);
+    return c64 ? launch_tile<float, Prog>(P, dev, mode, stream) : launch_tile<double, Prog>(P, dev, mode, stream);
 }
 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
                double *norm_out, void *ws, cudaStream_t stream) {
     if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
-    size_t entries = 0;
-    for (int i = 0; i < nops; ++i)
-        entries += ops[i].kind == QCS_OP_DENSE ? (size_t)1 << (2 * ops[i].k) : (size_t)1 << ops[i].k;
-    const size_t csize = dtype == QCS_C64 ? 8 : 16;
-    if (nops + 1 <= SmallProg::MAXOPS && (entries + 2) * csize <= sizeof(SmallProg::mats))
-        return build_and_launch<SmallProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
-    if (nops + 1 > LargeProg::MAXOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many ops in one fused pass");
+    if (nops <= 2) {
+        const int rc = build_and_launch<SmallProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
+        if (rc != QCS_ERR_UNSUPPORTED) return rc;
+    }
     return build_and_launch<LargeProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
 }
 

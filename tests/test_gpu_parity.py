@@ -18,7 +18,7 @@ from tests.util import TOL, oracle_apply, rand_state_vec, rand_unitary, rel_err
 pytestmark = pytest.mark.gpu
 
 DTYPES = [np.complex128, np.complex64]
-# 0 = cooperative staging, 1 = TMA bulk-copy pipeline (QCS_TEST_MODES narrows the set, e.g. "0")
+# 0 = cp.async ring (padded layout), 1 = TMA bulk-copy ring (QCS_TEST_MODES narrows the set, e.g. "0")
 MODES = [int(m) for m in os.environ.get('QCS_TEST_MODES', '0,1').split(',')]
 
 
@@ -485,7 +485,9 @@ def test_circuit_run_fused_matches_oracle(dtype, mode):
             assert rel_err(got.to_column_vector(), want) < tol, (n, max_ops)
         got = circ.run(s0, fuse=False)
         assert rel_err(got.to_column_vector(), want) < tol
-        assert np.array_equal(s0.to_column_vector(), np.eye(2 ** n)[0])     # argument untouched
+        basis0 = np.zeros(2 ** n)
+        basis0[0] = 1
+        assert np.array_equal(s0.to_column_vector(), basis0)     # argument untouched
         passes, gates = circ.stats(dtype)
         assert gates == len(orc.layered_circuit(n, depth)) and passes < gates
 
