@@ -40,24 +40,29 @@ struct TileOp {
 // register-level ops of a sweep
 constexpr int REGOP_U1 = 0;      // 2x2 matrix on register bit j
 constexpr int REGOP_PHASE = 1;   // multiply the amplitudes whose index matches (care, val) by one complex number
-constexpr int U1_GENERAL = 0, U1_REAL = 1, U1_RXLIKE = 2, U1_ANTIDIAG = 3;
-struct RegOp {
-    uint8_t code, j, form, reg_care, reg_val, pad0, pad1, pad2;   // reg_*: masks over the sweep's register bits
-    uint32_t base_care, base_val;                                 // tile-local index bits that are not register bits
-    uint64_t outer_care, outer_val;                               // flat-index bits outside the tile
-    int32_t mat, pad3;                                            // pool offset (U1: 4 entries row-major, PHASE: 1)
+constexpr int U1_GENERAL = 0, U1_REAL = 1, U1_RXLIKE = 2, U1_ANTIDIAG = 3, U1_SWAP = 4;
+constexpr int PHASE_GENERAL = 0, PHASE_NEG = 1;
+constexpr int MAX_OUTER_PREDS = 64;
+struct RegOp {                   // 16 bytes, read with one 128-bit shared-memory load
+    uint16_t code;               // kind | j << 2 | form << 4
+    uint8_t reg_care, reg_val;   // masks over the sweep's register bits
+    uint16_t base_care, base_val;// tile-local index bits that are not register bits (per-thread predicate)
+    int32_t mat;                 // pool offset (U1: 4 entries row-major, PHASE: 1)
+    int32_t outer_slot;          // -1, or index of the tile-uniform predicate this op depends on
 };
+struct OuterPred { uint64_t care, val; };   // flat-index bits outside the tile
 constexpr int SWEEP_REG = 0, SWEEP_GENERIC = 1;
 struct Sweep {
     int32_t kind, first, count, nreg;
     int8_t rpos[REG_BITS_MAX];       // tile-local positions of the register bits, ascending
-    int32_t pad;
+    int32_t thread_phase;            // some PHASE op of the sweep is uniform over a thread's amplitudes
 };
 
 template <int NSW, int NREG, int NGEN, int MATBYTES>
 struct TileProgram {
     static constexpr int MAX_SWEEPS = NSW, MAX_REGOPS = NREG, MAX_GENERIC = NGEN, MAT_BYTES = MATBYTES;
-    int32_t n, L, H, nsweeps, nregops, ngen, stages, mat_bytes;
+    int32_t n, L, H, nsweeps, nregops, ngen, nouter, stages, mat_bytes, scale_mode;
+    double gphase[2];                // pass-level complex factor (global phases of diagonal gates)
     int32_t hbits[TILE_MAX_H];
     uint64_t ntiles;
     const void *src;
@@ -67,11 +72,12 @@ struct TileProgram {
     void *ws;
     Sweep sweeps[NSW];
     RegOp regops[NREG];
+    OuterPred outer[MAX_OUTER_PREDS];
     TileOp gen[NGEN];
     alignas(16) unsigned char mats[MATBYTES];
 };
 using SmallProg = TileProgram<4, 34, 2, 4096 + 64>;
-using LargeProg = TileProgram<72, 200, QCS_MAX_OPS, 12288>;
+using LargeProg = TileProgram<72, 260, QCS_MAX_OPS, 12288>;
 static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes");
 
 struct DeviceInfo { int sms; size_t smem_per_sm; };

@@ -103,9 +103,13 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 // ------------------------------------------------------------------------------------------------
 // register sweeps
 // ------------------------------------------------------------------------------------------------
-template <typename R, int NX, int J>
-__device__ __forceinline__ void u1_butterfly(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
-                                             int form, uint32_t rc, uint32_t rv, bool tp) {
+// One 2x2 gate on register bit J of the 2^RB amplitudes a thread holds.  FORM picks the arithmetic
+// (general complex / real matrix / real diagonal + imaginary off-diagonal / anti-diagonal / X swap),
+// CTRL adds the control predicates: (x & rc) == rv over the register bits (uniform across the CTA)
+// and tp (per thread).
+template <typename R, int NX, int J, int FORM, bool CTRL>
+__device__ __forceinline__ void u1_apply(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
+                                         uint32_t rc, uint32_t rv, bool tp) {
     using C = typename CxT<R>::T;
     constexpr uint32_t BIT = 1u << J;
     const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
@@ -113,18 +117,20 @@ __device__ __forceinline__ void u1_butterfly(typename CxT<R>::T (&a)[NX], const 
     for (uint32_t x0 = 0; x0 < NX; ++x0) {
         if (x0 & BIT) continue;
         const uint32_t x1 = x0 | BIT;
-        if (((x0 & rc) == rv) && tp) {        // first part uniform across the CTA, second per thread
+        if (!CTRL || (((x0 & rc) == rv) && tp)) {
             const C t0 = a[x0], t1 = a[x1];
             C r0, r1;
-            if (form == U1_REAL) {
+            if (FORM == U1_REAL) {
                 r0.x = fma(m00.x, t0.x, m01.x * t1.x); r0.y = fma(m00.x, t0.y, m01.x * t1.y);
                 r1.x = fma(m10.x, t0.x, m11.x * t1.x); r1.y = fma(m10.x, t0.y, m11.x * t1.y);
-            } else if (form == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
+            } else if (FORM == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
                 r0.x = fma(m00.x, t0.x, -m01.y * t1.y); r0.y = fma(m00.x, t0.y, m01.y * t1.x);
                 r1.x = fma(m11.x, t1.x, -m10.y * t0.y); r1.y = fma(m11.x, t1.y, m10.y * t0.x);
-            } else if (form == U1_ANTIDIAG) {
+            } else if (FORM == U1_ANTIDIAG) {
                 r0 = cmul(m01, t1);
                 r1 = cmul(m10, t0);
+            } else if (FORM == U1_SWAP) {
+                r0 = t1; r1 = t0;
             } else {
                 r0 = cmul(m00, t0); cfma(r0, m01, t1);
                 r1 = cmul(m10, t0); cfma(r1, m11, t1);
@@ -134,9 +140,31 @@ __device__ __forceinline__ void u1_butterfly(typename CxT<R>::T (&a)[NX], const 
     }
 }
 
+template <typename R, int NX, int J>
+__device__ __forceinline__ void u1_dispatch(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
+                                            int form, bool ctrl, uint32_t rc, uint32_t rv, bool tp) {
+    if (!ctrl) {
+        switch (form) {
+            case U1_REAL: u1_apply<R, NX, J, U1_REAL, false>(a, M, 0, 0, true); break;
+            case U1_RXLIKE: u1_apply<R, NX, J, U1_RXLIKE, false>(a, M, 0, 0, true); break;
+            case U1_ANTIDIAG: u1_apply<R, NX, J, U1_ANTIDIAG, false>(a, M, 0, 0, true); break;
+            case U1_SWAP: u1_apply<R, NX, J, U1_SWAP, false>(a, M, 0, 0, true); break;
+            default: u1_apply<R, NX, J, U1_GENERAL, false>(a, M, 0, 0, true); break;
+        }
+    } else {
+        switch (form) {
+            case U1_REAL: u1_apply<R, NX, J, U1_REAL, true>(a, M, rc, rv, tp); break;
+            case U1_RXLIKE: u1_apply<R, NX, J, U1_RXLIKE, true>(a, M, rc, rv, tp); break;
+            case U1_ANTIDIAG: u1_apply<R, NX, J, U1_ANTIDIAG, true>(a, M, rc, rv, tp); break;
+            case U1_SWAP: u1_apply<R, NX, J, U1_SWAP, true>(a, M, rc, rv, tp); break;
+            default: u1_apply<R, NX, J, U1_GENERAL, true>(a, M, rc, rv, tp); break;
+        }
+    }
+}
+
 template <typename R, int RB, typename Layout>
 __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const Sweep &sw, const RegOp *rops,
-                                          const typename CxT<R>::T *pool, uint64_t tile_base, int tid, int nt) {
+                                          const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
     using C = typename CxT<R>::T;
     constexpr int NX = 1 << RB;
     const int nreg = sw.nreg;
@@ -146,6 +174,8 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
     for (int j = 0; j < RB; ++j) ps[j] = j < nreg ? Layout::amp(1u << sw.rpos[j]) : 0u;
     const bool pair_vec = (sizeof(C) == 8) && nreg >= 1 && sw.rpos[0] == 0;   // complex64 pairs as one 128-bit access
     const uint32_t ngroups = 1u << (m - nreg);
+    const int nops = sw.count;
+    const uint4 *ops4 = reinterpret_cast<const uint4 *>(rops + sw.first);
     for (uint32_t g = tid; g < ngroups; g += nt) {
         uint32_t base = g;
         for (int j = 0; j < nreg; ++j) base = insert_zero32(base, sw.rpos[j]);
@@ -174,33 +204,39 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
                 if (x < nx_used) a[x] = tile[addr[x]];
         }
         C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
-        bool have_ph = false;
-        for (int o = 0; o < sw.count; ++o) {
-            const RegOp &op = rops[sw.first + o];
-            if ((tile_base & op.outer_care) != op.outer_val) continue;           // tile-uniform
-            const bool tp = (base & op.base_care) == op.base_val;                // per thread
-            const uint32_t rc = op.reg_care, rv = op.reg_val;
-            if (op.code == REGOP_PHASE) {
-                const C d = pool[op.mat];
+        for (int o = 0; o < nops; ++o) {
+            const uint4 w = ops4[o];                         // one broadcast 128-bit load per op
+            const int slot = (int)w.w;
+            if (slot >= 0 && !((outer_ok >> slot) & 1ull)) continue;             // tile-uniform predicate
+            const uint32_t code = w.x & 0xffffu, rc = (w.x >> 16) & 0xffu, rv = w.x >> 24;
+            const uint32_t bcare = w.y & 0xffffu, bval = w.y >> 16;
+            const bool tp = (base & bcare) == bval;                              // per-thread predicate
+            const C *M = pool + (int)w.z;
+            const int form = (int)(code >> 4);
+            if ((code & 3u) == REGOP_PHASE) {
+                const C d = M[0];
                 if (rc == 0) {
-                    if (tp) { ph = cmul(d, ph); have_ph = true; }
+                    if (tp) ph = form == PHASE_NEG ? cx<R>(-ph.x, -ph.y) : cmul(d, ph);
+                } else if (form == PHASE_NEG) {
+#pragma unroll
+                    for (uint32_t x = 0; x < NX; ++x)
+                        if (((x & rc) == rv) && tp) { a[x].x = -a[x].x; a[x].y = -a[x].y; }
                 } else {
 #pragma unroll
                     for (uint32_t x = 0; x < NX; ++x)
                         if (((x & rc) == rv) && tp) a[x] = cmul(d, a[x]);
                 }
             } else {
-                const C *M = pool + op.mat;
-                const int form = op.form;
-                switch (op.j) {
-                    case 0: u1_butterfly<R, NX, 0>(a, M, form, rc, rv, tp); break;
-                    case 1: if (RB > 1) u1_butterfly<R, NX, (RB > 1 ? 1 : 0)>(a, M, form, rc, rv, tp); break;
-                    case 2: if (RB > 2) u1_butterfly<R, NX, (RB > 2 ? 2 : 0)>(a, M, form, rc, rv, tp); break;
-                    default: if (RB > 3) u1_butterfly<R, NX, (RB > 3 ? 3 : 0)>(a, M, form, rc, rv, tp); break;
+                const bool ctrl = (rc | bcare) != 0;
+                switch ((code >> 2) & 3u) {
+                    case 0: u1_dispatch<R, NX, 0>(a, M, form, ctrl, rc, rv, tp); break;
+                    case 1: u1_dispatch<R, NX, (RB > 1 ? 1 : 0)>(a, M, form, ctrl, rc, rv, tp); break;
+                    case 2: u1_dispatch<R, NX, (RB > 2 ? 2 : 0)>(a, M, form, ctrl, rc, rv, tp); break;
+                    default: u1_dispatch<R, NX, (RB > 3 ? 3 : 0)>(a, M, form, ctrl, rc, rv, tp); break;
                 }
             }
         }
-        if (have_ph) {
+        if (sw.thread_phase) {
 #pragma unroll
             for (uint32_t x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
         }
@@ -225,9 +261,11 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
 struct ProgView {
     const Sweep *sweeps;
     const RegOp *regops;
+    const OuterPred *outer;
     const TileOp *gen;
     const void *pool;
-    int nsweeps;
+    uint64_t *outer_ok;     // [2]: per-tile bitmask of the outer predicates, double-buffered by tile parity
+    int nsweeps, nouter;
 };
 
 __host__ __device__ __forceinline__ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -236,8 +274,8 @@ __host__ __device__ __forceinline__ uint32_t align128(uint32_t x) { return (x + 
 template <typename Prog>
 static uint32_t program_smem_bytes(const Prog &P) {
     return align128(align16(P.nsweeps * (uint32_t)sizeof(Sweep)) + align16(P.nregops * (uint32_t)sizeof(RegOp)) +
-                    align16(P.ngen * (uint32_t)sizeof(TileOp)) + align16((uint32_t)P.mat_bytes) +
-                    (uint32_t)sizeof(uint64_t) * (1u << P.H));
+                    align16(P.nouter * (uint32_t)sizeof(OuterPred)) + align16(P.ngen * (uint32_t)sizeof(TileOp)) +
+                    align16((uint32_t)P.mat_bytes) + 16u + (uint32_t)sizeof(uint64_t) * (1u << P.H));
 }
 
 __device__ __forceinline__ void copy_words(void *dst, const void *src, uint32_t bytes, int tid, int nt) {
@@ -257,12 +295,17 @@ __device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Pro
     pv.regops = reinterpret_cast<const RegOp *>(smem + o);
     copy_words(smem + o, P.regops, P.nregops * (uint32_t)sizeof(RegOp), tid, nt);
     o += align16(P.nregops * (uint32_t)sizeof(RegOp));
+    pv.outer = reinterpret_cast<const OuterPred *>(smem + o);
+    copy_words(smem + o, P.outer, P.nouter * (uint32_t)sizeof(OuterPred), tid, nt);
+    o += align16(P.nouter * (uint32_t)sizeof(OuterPred));
     pv.gen = reinterpret_cast<const TileOp *>(smem + o);
     copy_words(smem + o, P.gen, P.ngen * (uint32_t)sizeof(TileOp), tid, nt);
     o += align16(P.ngen * (uint32_t)sizeof(TileOp));
     pv.pool = smem + o;
     copy_words(smem + o, P.mats, (uint32_t)P.mat_bytes, tid, nt);
     o += align16((uint32_t)P.mat_bytes);
+    pv.outer_ok = reinterpret_cast<uint64_t *>(smem + o);
+    o += 16u;
     uint64_t *co = reinterpret_cast<uint64_t *>(smem + o);
     for (uint32_t c = tid; c < (1u << P.H); c += nt) {
         uint64_t off = 0;
@@ -273,18 +316,32 @@ __device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Pro
     chunk_off = co;
     o += (uint32_t)sizeof(uint64_t) * (1u << P.H);
     pv.nsweeps = P.nsweeps;
+    pv.nouter = P.nouter;
     return align128(o);
+}
+
+// warp 0 evaluates the tile-uniform predicates of tile `tile_base` into pv.outer_ok[parity]
+__device__ __forceinline__ void eval_outer(const ProgView &pv, uint64_t tile_base, int parity, int tid) {
+    if (pv.nouter == 0 || tid >= 32) return;
+    uint64_t mask = 0;
+    for (int r = 0; r < pv.nouter; r += 32) {
+        const int i = r + tid;
+        const bool ok = i < pv.nouter && (tile_base & pv.outer[i].care) == pv.outer[i].val;
+        mask |= (uint64_t)__ballot_sync(0xffffffffu, ok) << r;
+    }
+    if (tid == 0) pv.outer_ok[parity] = mask;
 }
 
 template <typename R, typename Layout>
 __device__ __forceinline__ void run_program(typename CxT<R>::T *tile, const ProgView &pv, int m, uint64_t tile_base,
-                                            int tid, int nt) {
+                                            int parity, int tid, int nt) {
     using C = typename CxT<R>::T;
     constexpr int RB = sizeof(C) == 8 ? REG_BITS_C64 : REG_BITS_C128;
     const C *pool = reinterpret_cast<const C *>(pv.pool);
+    const uint64_t outer_ok = pv.nouter ? pv.outer_ok[parity] : 0ull;
     for (int s = 0; s < pv.nsweeps; ++s) {
         const Sweep &sw = pv.sweeps[s];
-        if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout>(tile, m, sw, pv.regops, pool, tile_base, tid, nt);
+        if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout>(tile, m, sw, pv.regops, pool, outer_ok, tid, nt);
         else apply_generic<R, Layout>(tile, m, pv.gen[sw.first], pool, tile_base, tid, nt);
         __syncthreads();
     }
@@ -339,6 +396,32 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {   // n = groups a
     }
 }
 
+// complex factor applied to a 16-byte vector of amplitudes while it streams out
+template <typename R> __device__ __forceinline__ uint4 vec_cscale(const uint4 v, R fr, R fi);
+template <> __device__ __forceinline__ uint4 vec_cscale<float>(const uint4 v, float fr, float fi) {
+    const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z), d = __uint_as_float(v.w);
+    uint4 r;
+    r.x = __float_as_uint(fmaf(fr, a, -fi * b)); r.y = __float_as_uint(fmaf(fr, b, fi * a));
+    r.z = __float_as_uint(fmaf(fr, c, -fi * d)); r.w = __float_as_uint(fmaf(fr, d, fi * c));
+    return r;
+}
+template <> __device__ __forceinline__ uint4 vec_cscale<double>(const uint4 v, double fr, double fi) {
+    const double a = __hiloint2double(v.y, v.x), b = __hiloint2double(v.w, v.z);
+    const double re = fma(fr, a, -fi * b), im = fma(fr, b, fi * a);
+    uint4 r;
+    r.x = __double2loint(re); r.y = __double2hiint(re); r.z = __double2loint(im); r.w = __double2hiint(im);
+    return r;
+}
+// squared magnitude of a vector in the accumulation type of the tile-local partial sum
+__device__ __forceinline__ void vec_norm_acc(float &acc, const uint4 v, float) {
+    const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z), d = __uint_as_float(v.w);
+    acc = fmaf(a, a, acc); acc = fmaf(b, b, acc); acc = fmaf(c, c, acc); acc = fmaf(d, d, acc);
+}
+__device__ __forceinline__ void vec_norm_acc(double &acc, const uint4 v, double) {
+    const double a = __hiloint2double(v.y, v.x), b = __hiloint2double(v.w, v.z);
+    acc = fma(a, a, acc); acc = fma(b, b, acc);
+}
+
 template <typename R, typename Prog>
 __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid_constant__ Prog P) {
     using C = typename CxT<R>::T;
@@ -353,47 +436,72 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid
     const int S = P.stages;
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(m);
     constexpr int VSHIFT = sizeof(C) == 8 ? 1 : 0;       // amplitudes per 16-byte vector = 1 << VSHIFT
-    const uint32_t tile_vecs = (1u << m) >> VSHIFT;
-    const int chunk_vec_bits = P.L - VSHIFT;             // log2(vectors per chunk)
-    const uint32_t chunk_vec_mask = (1u << chunk_vec_bits) - 1u;
-    const bool rescale = P.norm_in != nullptr;
-    const R scale = (R)load_inv_norm(P.norm_in);
+    const uint32_t nchunks = 1u << P.H;
+    const uint32_t chunk_vecs = (1u << P.L) >> VSHIFT;   // 16-byte vectors per contiguous chunk
+    const uint32_t chunk_svecs = Layout::vec(chunk_vecs);// ... and their padded extent in shared memory
+    // this thread's vectors inside a chunk: w = tid, tid + nt, ... ; the padded map is additive over
+    // the disjoint bit ranges of tid and the stride, so both addresses advance by constants
+    const uint32_t svec_tid = Layout::vec((uint32_t)tid);
+    const uint32_t svec_step = Layout::vec((uint32_t)nt);
+    const int scale_mode = P.scale_mode;                 // 0 none, 1 real, 2 complex
+    R fr = R(1), fi = R(0);
+    if (scale_mode) {
+        const double s = load_inv_norm(P.norm_in);
+        fr = (R)(s * P.gphase[0]); fi = (R)(s * P.gphase[1]);
+    }
     const uint4 *src = reinterpret_cast<const uint4 *>(P.src);
     uint4 *dst = reinterpret_cast<uint4 *>(P.dst);
     double nacc[1] = {0.0};
     const uint64_t my_tiles = (P.ntiles > blockIdx.x) ? (P.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     __syncthreads();   // program + chunk table visible
 
-    auto issue_load = [&](uint64_t it) {
+    auto issue_load = [&](uint64_t it, int st) {
         const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
-        uint4 *stage = reinterpret_cast<uint4 *>(ring + (size_t)(it % S) * stage_bytes);
-        for (uint32_t v = tid; v < tile_vecs; v += nt) {
-            const uint64_t g = ((base + chunk_off[v >> chunk_vec_bits]) >> VSHIFT) + (v & chunk_vec_mask);
-            cp_async16(&stage[Layout::vec(v)], &src[g]);
+        const uint32_t stage_u32 = smem_u32(ring + (size_t)st * stage_bytes);
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            const uint4 *gp = src + ((base + chunk_off[c]) >> VSHIFT) + tid;
+            uint32_t sp = stage_u32 + (c * chunk_svecs + svec_tid) * 16u;
+            for (uint32_t w = tid; w < chunk_vecs; w += nt) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+                gp += nt;
+                sp += svec_step * 16u;
+            }
         }
     };
 
     for (int s = 0; s < S - 1; ++s) {
-        if ((uint64_t)s < my_tiles) issue_load(s);
+        if ((uint64_t)s < my_tiles) issue_load(s, s);
         cp_async_commit();
     }
+    int st = 0, st_next = S - 1;       // stage of tile `it`, stage the prefetch goes to
     for (uint64_t it = 0; it < my_tiles; ++it) {
+        const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
+        eval_outer(pv, base, (int)(it & 1), tid);
         cp_async_wait_pending(S - 2);      // this thread's copies of tile `it` have landed
         __syncthreads();                   // ... everyone's have, and stage (it-1)%S is drained
         const uint64_t nxt = it + (uint64_t)(S - 1);
-        if (nxt < my_tiles) issue_load(nxt);
+        if (nxt < my_tiles) issue_load(nxt, st_next);
         cp_async_commit();
-        const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
-        unsigned char *stage = ring + (size_t)(it % S) * stage_bytes;
-        run_program<R, Layout>(reinterpret_cast<C *>(stage), pv, m, base, tid, nt);
-        const uint4 *stage_v = reinterpret_cast<const uint4 *>(stage);
-        for (uint32_t v = tid; v < tile_vecs; v += nt) {
-            const uint64_t g = ((base + chunk_off[v >> chunk_vec_bits]) >> VSHIFT) + (v & chunk_vec_mask);
-            uint4 val = stage_v[Layout::vec(v)];
-            if (rescale) val = vec_scale<R>(val, scale);
-            nacc[0] += vec_abs2<R>(val);
-            dst[g] = val;
+        unsigned char *stage = ring + (size_t)st * stage_bytes;
+        run_program<R, Layout>(reinterpret_cast<C *>(stage), pv, m, base, (int)(it & 1), tid, nt);
+        // stream the tile out: fold the lazy scale / global phase, accumulate the squared norm
+        R tacc = R(0);
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            uint4 *gp = dst + ((base + chunk_off[c]) >> VSHIFT) + tid;
+            const uint4 *sp = reinterpret_cast<const uint4 *>(stage) + (c * chunk_svecs + svec_tid);
+            for (uint32_t w = tid; w < chunk_vecs; w += nt) {
+                uint4 val = *sp;
+                if (scale_mode == 1) val = vec_scale<R>(val, fr);
+                else if (scale_mode == 2) val = vec_cscale<R>(val, fr, fi);
+                vec_norm_acc(tacc, val, R(0));
+                *gp = val;
+                gp += nt;
+                sp += svec_step;
+            }
         }
+        nacc[0] += (double)tacc;
+        st = st + 1 == S ? 0 : st + 1;
+        st_next = st_next + 1 == S ? 0 : st_next + 1;
     }
     cp_async_wait_pending(0);
     if (P.norm_out) grid_sum_publish<1>(nacc, P.ws, P.norm_out);
@@ -459,8 +567,12 @@ __global__ void __launch_bounds__(TILE_THREADS_BULK, 1) tile_kernel_bulk(const _
     const uint32_t tile_bytes = (uint32_t)((sizeof(C)) << m);
     const uint32_t chunk_bytes = (uint32_t)((sizeof(C)) << P.L);
     const uint32_t nchunks = 1u << P.H;
-    const bool rescale = P.norm_in != nullptr;
-    const R scale = (R)load_inv_norm(P.norm_in);
+    const int scale_mode = P.scale_mode;
+    R fr = R(1), fi = R(0);
+    if (scale_mode) {
+        const double s = load_inv_norm(P.norm_in);
+        fr = (R)(s * P.gphase[0]); fi = (R)(s * P.gphase[1]);
+    }
     const unsigned char *src = reinterpret_cast<const unsigned char *>(P.src);
     unsigned char *dst = reinterpret_cast<unsigned char *>(P.dst);
     double nacc[1] = {0.0};
@@ -490,16 +602,21 @@ __global__ void __launch_bounds__(TILE_THREADS_BULK, 1) tile_kernel_bulk(const _
         const uint32_t parity = (uint32_t)((it / S) & 1);
         const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
         C *tile = reinterpret_cast<C *>(ring + (size_t)st * tile_bytes);
+        eval_outer(pv, base, (int)(it & 1), tid);
         mbar_wait(&full_bar[st], parity);
-        run_program<R, Layout>(tile, pv, m, base, tid, nt);
-        if (P.norm_out || rescale) {
+        if (pv.nouter) __syncthreads();
+        run_program<R, Layout>(tile, pv, m, base, (int)(it & 1), tid, nt);
+        if (P.norm_out || scale_mode) {
             uint4 *tv = reinterpret_cast<uint4 *>(tile);
             const uint32_t tile_vecs = tile_bytes >> 4;
+            R tacc = R(0);
             for (uint32_t v = tid; v < tile_vecs; v += nt) {
                 uint4 val = tv[v];
-                if (rescale) { val = vec_scale<R>(val, scale); tv[v] = val; }
-                nacc[0] += vec_abs2<R>(val);
+                if (scale_mode == 1) { val = vec_scale<R>(val, fr); tv[v] = val; }
+                else if (scale_mode == 2) { val = vec_cscale<R>(val, fr, fi); tv[v] = val; }
+                vec_norm_acc(tacc, val, R(0));
             }
+            nacc[0] += (double)tacc;
         }
         fence_proxy_async();   // generic-proxy writes of this stage -> visible to the bulk store
         __syncthreads();
@@ -685,7 +802,8 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     int pending[QCS_MAX_OPS];
     int npend = nops;
     for (int i = 0; i < nops; ++i) pending[i] = i;
-    P.nsweeps = P.nregops = P.ngen = 0;
+    P.nsweeps = P.nregops = P.ngen = P.nouter = 0;
+    P.gphase[0] = 1.0; P.gphase[1] = 0.0;
     while (npend > 0) {
         if (P.nsweeps >= Prog::MAX_SWEEPS) return set_error(QCS_ERR_UNSUPPORTED, "too many sweeps in one pass");
         Sweep &sw = P.sweeps[P.nsweeps];
@@ -736,7 +854,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         }
         for (int b = m - 1; b >= 0 && S_count < nreg; --b)
             if (!(S_local & (1u << b))) { S_local |= 1u << b; ++S_count; }
-        sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg;
+        sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg; sw.thread_phase = 0;
         int8_t reg_index_of_local[32];
         for (int b = 0, j = 0; b < 32; ++b) {
             reg_index_of_local[b] = -1;
@@ -746,10 +864,21 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 ++j;
             }
         }
-        auto split_masks = [&](uint64_t care, uint64_t val, RegOp &r) {
-            // flat-index (care, val) -> register / thread / tile parts
-            r.outer_care = care & ~tile_mask; r.outer_val = val & ~tile_mask;
-            r.reg_care = r.reg_val = 0; r.base_care = r.base_val = 0;
+        // flat-index (care, val) -> register / thread / tile parts of a RegOp; false if out of slots
+        auto split_masks = [&](uint64_t care, uint64_t val, RegOp &r) -> bool {
+            r.reg_care = r.reg_val = 0; r.base_care = r.base_val = 0; r.outer_slot = -1;
+            const uint64_t oc = care & ~tile_mask, ov = val & ~tile_mask;
+            if (oc) {
+                int slot = -1;
+                for (int i = 0; i < P.nouter; ++i)
+                    if (P.outer[i].care == oc && P.outer[i].val == ov) { slot = i; break; }
+                if (slot < 0) {
+                    if (P.nouter >= MAX_OUTER_PREDS) return false;
+                    slot = P.nouter++;
+                    P.outer[slot].care = oc; P.outer[slot].val = ov;
+                }
+                r.outer_slot = slot;
+            }
             for (int b = 0; b < n; ++b) {
                 if (!(((care & tile_mask) >> b) & 1ull)) continue;
                 const int lb = local_of(b);
@@ -758,42 +887,62 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     r.reg_care |= (uint8_t)(1u << reg_index_of_local[lb]);
                     if (one) r.reg_val |= (uint8_t)(1u << reg_index_of_local[lb]);
                 } else {
-                    r.base_care |= 1u << lb;
-                    if (one) r.base_val |= 1u << lb;
+                    r.base_care |= (uint16_t)(1u << lb);
+                    if (one) r.base_val |= (uint16_t)(1u << lb);
                 }
             }
+            return true;
         };
         for (int t = 0; t < ntaken; ++t) {
             const qcs_op &o = ops[taken[t]];
             if (hop[taken[t]].kind == 0) {
                 if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
                 RegOp &r = P.regops[P.nregops++];
-                r.code = REGOP_U1;
-                r.j = (uint8_t)reg_index_of_local[local_of(o.bitpos[0])];
+                const int j = reg_index_of_local[local_of(o.bitpos[0])];
                 const double *M = o.matrix;   // m00 m01 m10 m11 as (re, im)
                 const bool real = M[1] == 0 && M[3] == 0 && M[5] == 0 && M[7] == 0;
                 const bool rxl = M[1] == 0 && M[7] == 0 && M[2] == 0 && M[4] == 0;
                 const bool anti = M[0] == 0 && M[1] == 0 && M[6] == 0 && M[7] == 0;
-                r.form = (uint8_t)(real ? U1_REAL : anti ? U1_ANTIDIAG : rxl ? U1_RXLIKE : U1_GENERAL);
-                split_masks(o.ctrl_mask, o.ctrl_mask, r);
+                const bool swp = anti && M[2] == 1 && M[3] == 0 && M[4] == 1 && M[5] == 0;
+                const int form = swp ? U1_SWAP : real ? U1_REAL : anti ? U1_ANTIDIAG : rxl ? U1_RXLIKE : U1_GENERAL;
+                r.code = (uint16_t)(REGOP_U1 | (j << 2) | (form << 4));
+                if (!split_masks(o.ctrl_mask, o.ctrl_mask, r))
+                    return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
                 const int at = push_entries(M, 4);
                 if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
                 r.mat = at;
                 ++sw.count;
             } else {
-                // diagonal on k bits: one phase op per basis pattern whose entry is not exactly 1
+                // diagonal on k bits.  An uncontrolled diagonal is d[0] * diag(1, d[x]/d[0], ...): the common
+                // factor goes to the pass-level phase, and patterns whose entry is exactly 1 cost nothing.
+                double d0r = 1.0, d0i = 0.0;
+                if (o.ctrl_mask == 0 && !(o.matrix[0] == 1.0 && o.matrix[1] == 0.0) &&
+                    (o.matrix[0] != 0.0 || o.matrix[1] != 0.0)) {
+                    d0r = o.matrix[0]; d0i = o.matrix[1];
+                    const double gr = P.gphase[0] * d0r - P.gphase[1] * d0i, gi = P.gphase[0] * d0i + P.gphase[1] * d0r;
+                    P.gphase[0] = gr; P.gphase[1] = gi;
+                }
+                const double d0n = d0r * d0r + d0i * d0i;
                 for (int x = 0; x < (1 << o.k); ++x) {
-                    const double re = o.matrix[2 * x], im = o.matrix[2 * x + 1];
+                    double re = o.matrix[2 * x], im = o.matrix[2 * x + 1];
+                    if (d0r != 1.0 || d0i != 0.0) {
+                        if (x == 0) continue;
+                        const double qr = (re * d0r + im * d0i) / d0n, qi = (im * d0r - re * d0i) / d0n;   // d[x] / d[0]
+                        re = qr; im = qi;
+                    }
                     if (re == 1.0 && im == 0.0) continue;
                     if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
                     RegOp &r = P.regops[P.nregops++];
-                    r.code = REGOP_PHASE; r.j = 0; r.form = 0;
+                    const int form = (re == -1.0 && im == 0.0) ? PHASE_NEG : PHASE_GENERAL;
+                    r.code = (uint16_t)(REGOP_PHASE | (form << 4));
                     uint64_t care = o.ctrl_mask, val = o.ctrl_mask;
                     for (int j = 0; j < o.k; ++j) {
                         care |= 1ull << o.bitpos[j];
                         if ((x >> (o.k - 1 - j)) & 1) val |= 1ull << o.bitpos[j];
                     }
-                    split_masks(care, val, r);
+                    if (!split_masks(care, val, r))
+                        return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
+                    if (r.reg_care == 0) sw.thread_phase = 1;
                     const double d[2] = {re, im};
                     const int at = push_entries(d, 1);
                     if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
@@ -807,6 +956,8 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         npend = nrest;
     }
     P.mat_bytes = (int32_t)(used * csize);
+    const bool has_gphase = !(P.gphase[0] == 1.0 && P.gphase[1] == 0.0);
+    P.scale_mode = has_gphase ? 2 : (norm_in ? 1 : 0);
     const DeviceInfo &dev = device_info();
     const int mode = tile_mode();
     return c64 ? launch_tile<float, Prog>(P, dev, mode, stream) : launch_tile<double, Prog>(P, dev, mode, stream);

@@ -260,7 +260,9 @@ def _sample(ps, u=None):
     """Outcome index from the marginals: ``np.random.choice`` (one uniform from the global legacy
     stream, like state.py:364), or the same inverse-CDF rule on a caller-supplied uniform."""
     if u is None:
-        return int(np.random.choice(len(ps), p=ps))
+        # complex64 amplitudes sum to 1 only to ~1e-7, np.random.choice wants 1.5e-8: hand it the
+        # normalised vector (its own cdf /= cdf[-1] makes this a no-op for the outcome)
+        return int(np.random.choice(len(ps), p=ps / ps.sum()))
     cdf = np.cumsum(ps)
     cdf /= cdf[-1]
     return int(np.searchsorted(cdf, u, side='right'))
