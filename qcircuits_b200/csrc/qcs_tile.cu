@@ -162,23 +162,33 @@ __device__ __forceinline__ void u1_dispatch(typename CxT<R>::T (&a)[NX], const t
     }
 }
 
-template <typename R, int RB, typename Layout>
-__device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const Sweep &sw, const RegOp *rops,
-                                          const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
+// MT > 0: the tile has exactly MT bits, every sweep uses RB register bits (compile-time trip counts).
+// VEC   : complex64 with tile bit 0 among the register bits -> amplitude pairs move as one 128-bit access.
+template <typename R, int RB, typename Layout, int MT, bool VEC>
+__device__ __forceinline__ void reg_sweep_impl(typename CxT<R>::T *tile, int m_rt, const Sweep &sw, const RegOp *rops,
+                                               const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
     using C = typename CxT<R>::T;
     constexpr int NX = 1 << RB;
-    const int nreg = sw.nreg;
+    constexpr bool FAST = MT > 0;
+    const int m = FAST ? MT : m_rt;
+    const int nreg = FAST ? RB : sw.nreg;
     const uint32_t nx_used = 1u << nreg;
     uint32_t ps[RB];      // shared-memory stride of each register bit (layout maps are additive)
+    int rp[RB];
 #pragma unroll
-    for (int j = 0; j < RB; ++j) ps[j] = j < nreg ? Layout::amp(1u << sw.rpos[j]) : 0u;
-    const bool pair_vec = (sizeof(C) == 8) && nreg >= 1 && sw.rpos[0] == 0;   // complex64 pairs as one 128-bit access
+    for (int j = 0; j < RB; ++j) {
+        rp[j] = sw.rpos[j];
+        ps[j] = j < nreg ? Layout::amp(1u << rp[j]) : 0u;
+    }
     const uint32_t ngroups = 1u << (m - nreg);
     const int nops = sw.count;
     const uint4 *ops4 = reinterpret_cast<const uint4 *>(rops + sw.first);
+#pragma unroll
     for (uint32_t g = tid; g < ngroups; g += nt) {
         uint32_t base = g;
-        for (int j = 0; j < nreg; ++j) base = insert_zero32(base, sw.rpos[j]);
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+            if (j < nreg) base = insert_zero32(base, rp[j]);
         const uint32_t pb = Layout::amp(base);
         uint32_t addr[NX];
 #pragma unroll
@@ -190,10 +200,10 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
             addr[x] = o;
         }
         C a[NX];
-        if (pair_vec) {
+        if (VEC) {
 #pragma unroll
             for (uint32_t x = 0; x < NX; x += 2) {
-                if (x < nx_used) {
+                if (FAST || x < nx_used) {
                     const float4 v = *reinterpret_cast<const float4 *>(&tile[addr[x]]);
                     a[x].x = v.x; a[x].y = v.y; a[x + 1].x = v.z; a[x + 1].y = v.w;
                 }
@@ -201,7 +211,7 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
         } else {
 #pragma unroll
             for (uint32_t x = 0; x < NX; ++x)
-                if (x < nx_used) a[x] = tile[addr[x]];
+                if (FAST || x < nx_used) a[x] = tile[addr[x]];
         }
         C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
         for (int o = 0; o < nops; ++o) {
@@ -240,10 +250,10 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
 #pragma unroll
             for (uint32_t x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
         }
-        if (pair_vec) {
+        if (VEC) {
 #pragma unroll
             for (uint32_t x = 0; x < NX; x += 2) {
-                if (x < nx_used) {
+                if (FAST || x < nx_used) {
                     float4 v;
                     v.x = a[x].x; v.y = a[x].y; v.z = a[x + 1].x; v.w = a[x + 1].y;
                     *reinterpret_cast<float4 *>(&tile[addr[x]]) = v;
@@ -252,9 +262,19 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const
         } else {
 #pragma unroll
             for (uint32_t x = 0; x < NX; ++x)
-                if (x < nx_used) tile[addr[x]] = a[x];
+                if (FAST || x < nx_used) tile[addr[x]] = a[x];
         }
     }
+}
+
+template <typename R, int RB, typename Layout, int MT>
+__device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const Sweep &sw, const RegOp *rops,
+                                          const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
+    using C = typename CxT<R>::T;
+    if (sizeof(C) == 8 && sw.nreg >= 1 && sw.rpos[0] == 0)
+        reg_sweep_impl<R, RB, Layout, MT, sizeof(C) == 8>(tile, m, sw, rops, pool, outer_ok, tid, nt);
+    else
+        reg_sweep_impl<R, RB, Layout, MT, false>(tile, m, sw, rops, pool, outer_ok, tid, nt);
 }
 
 // The program as staged in shared memory.
@@ -332,7 +352,7 @@ __device__ __forceinline__ void eval_outer(const ProgView &pv, uint64_t tile_bas
     if (tid == 0) pv.outer_ok[parity] = mask;
 }
 
-template <typename R, typename Layout>
+template <typename R, typename Layout, int MT>
 __device__ __forceinline__ void run_program(typename CxT<R>::T *tile, const ProgView &pv, int m, uint64_t tile_base,
                                             int parity, int tid, int nt) {
     using C = typename CxT<R>::T;
@@ -341,7 +361,7 @@ __device__ __forceinline__ void run_program(typename CxT<R>::T *tile, const Prog
     const uint64_t outer_ok = pv.nouter ? pv.outer_ok[parity] : 0ull;
     for (int s = 0; s < pv.nsweeps; ++s) {
         const Sweep &sw = pv.sweeps[s];
-        if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout>(tile, m, sw, pv.regops, pool, outer_ok, tid, nt);
+        if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout, MT>(tile, m, sw, pv.regops, pool, outer_ok, tid, nt);
         else apply_generic<R, Layout>(tile, m, pv.gen[sw.first], pool, tile_base, tid, nt);
         __syncthreads();
     }
@@ -422,22 +442,29 @@ __device__ __forceinline__ void vec_norm_acc(double &acc, const uint4 v, double)
     acc = fma(a, a, acc); acc = fma(b, b, acc);
 }
 
-template <typename R, typename Prog>
+// MT > 0: compile-time geometry -- the tile has MT bits, its low LSTD bits are contiguous, the CTA has
+// TILE_THREADS threads; every staging loop has a constant trip count.  MT == 0: everything at run time
+// (small states, unusual tiles).
+template <typename R, typename Prog, int MT>
 __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid_constant__ Prog P) {
     using C = typename CxT<R>::T;
     using Layout = PaddedLayout<C>;
+    constexpr bool FAST = MT > 0;
+    constexpr int LSTD = sizeof(C) == 8 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
+    constexpr int VSHIFT = sizeof(C) == 8 ? 1 : 0;       // amplitudes per 16-byte vector = 1 << VSHIFT
     extern __shared__ __align__(128) unsigned char smem_all[];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x;
+    const int nt = FAST ? TILE_THREADS : (int)blockDim.x;
     ProgView pv;
     const uint64_t *chunk_off;
     const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, nt);
     unsigned char *ring = smem_all + prog_bytes;
-    const int m = P.L + P.H;
+    const int L = FAST ? LSTD : P.L;
+    const int m = FAST ? MT : P.L + P.H;
     const int S = P.stages;
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(m);
-    constexpr int VSHIFT = sizeof(C) == 8 ? 1 : 0;       // amplitudes per 16-byte vector = 1 << VSHIFT
-    const uint32_t nchunks = 1u << P.H;
-    const uint32_t chunk_vecs = (1u << P.L) >> VSHIFT;   // 16-byte vectors per contiguous chunk
+    const uint32_t nchunks = 1u << (m - L);
+    const uint32_t chunk_vecs = (1u << L) >> VSHIFT;     // 16-byte vectors per contiguous chunk
     const uint32_t chunk_svecs = Layout::vec(chunk_vecs);// ... and their padded extent in shared memory
     // this thread's vectors inside a chunk: w = tid, tid + nt, ... ; the padded map is additive over
     // the disjoint bit ranges of tid and the stride, so both addresses advance by constants
@@ -449,20 +476,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid
         const double s = load_inv_norm(P.norm_in);
         fr = (R)(s * P.gphase[0]); fi = (R)(s * P.gphase[1]);
     }
-    const uint4 *src = reinterpret_cast<const uint4 *>(P.src);
-    uint4 *dst = reinterpret_cast<uint4 *>(P.dst);
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.src) + tid;
+    uint4 *dst = reinterpret_cast<uint4 *>(P.dst) + tid;
     double nacc[1] = {0.0};
     const uint64_t my_tiles = (P.ntiles > blockIdx.x) ? (P.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     __syncthreads();   // program + chunk table visible
 
     auto issue_load = [&](uint64_t it, int st) {
         const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
-        const uint32_t stage_u32 = smem_u32(ring + (size_t)st * stage_bytes);
+        const uint32_t stage_u32 = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
+#pragma unroll
         for (uint32_t c = 0; c < nchunks; ++c) {
-            const uint4 *gp = src + ((base + chunk_off[c]) >> VSHIFT) + tid;
-            uint32_t sp = stage_u32 + (c * chunk_svecs + svec_tid) * 16u;
-            for (uint32_t w = tid; w < chunk_vecs; w += nt) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+            const uint4 *gp = src + ((base + chunk_off[c]) >> VSHIFT);
+            uint32_t sp = stage_u32 + c * chunk_svecs * 16u;
+#pragma unroll
+            for (uint32_t w = 0; w < chunk_vecs; w += nt) {
+                if (FAST || w + tid < chunk_vecs)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
                 gp += nt;
                 sp += svec_step * 16u;
             }
@@ -483,18 +513,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid
         if (nxt < my_tiles) issue_load(nxt, st_next);
         cp_async_commit();
         unsigned char *stage = ring + (size_t)st * stage_bytes;
-        run_program<R, Layout>(reinterpret_cast<C *>(stage), pv, m, base, (int)(it & 1), tid, nt);
+        run_program<R, Layout, MT>(reinterpret_cast<C *>(stage), pv, m, base, (int)(it & 1), tid, nt);
         // stream the tile out: fold the lazy scale / global phase, accumulate the squared norm
         R tacc = R(0);
+        const uint4 *sbase = reinterpret_cast<const uint4 *>(stage) + svec_tid;
+#pragma unroll
         for (uint32_t c = 0; c < nchunks; ++c) {
-            uint4 *gp = dst + ((base + chunk_off[c]) >> VSHIFT) + tid;
-            const uint4 *sp = reinterpret_cast<const uint4 *>(stage) + (c * chunk_svecs + svec_tid);
-            for (uint32_t w = tid; w < chunk_vecs; w += nt) {
-                uint4 val = *sp;
-                if (scale_mode == 1) val = vec_scale<R>(val, fr);
-                else if (scale_mode == 2) val = vec_cscale<R>(val, fr, fi);
-                vec_norm_acc(tacc, val, R(0));
-                *gp = val;
+            uint4 *gp = dst + ((base + chunk_off[c]) >> VSHIFT);
+            const uint4 *sp = sbase + c * chunk_svecs;
+#pragma unroll
+            for (uint32_t w = 0; w < chunk_vecs; w += nt) {
+                if (FAST || w + tid < chunk_vecs) {
+                    uint4 val = *sp;
+                    if (scale_mode == 1) val = vec_scale<R>(val, fr);
+                    else if (scale_mode == 2) val = vec_cscale<R>(val, fr, fi);
+                    vec_norm_acc(tacc, val, R(0));
+                    *gp = val;
+                }
                 gp += nt;
                 sp += svec_step;
             }
@@ -605,7 +640,7 @@ __global__ void __launch_bounds__(TILE_THREADS_BULK, 1) tile_kernel_bulk(const _
         eval_outer(pv, base, (int)(it & 1), tid);
         mbar_wait(&full_bar[st], parity);
         if (pv.nouter) __syncthreads();
-        run_program<R, Layout>(tile, pv, m, base, (int)(it & 1), tid, nt);
+        run_program<R, Layout, 0>(tile, pv, m, base, (int)(it & 1), tid, nt);
         if (P.norm_out || scale_mode) {
             uint4 *tv = reinterpret_cast<uint4 *>(tile);
             const uint32_t tile_vecs = tile_bytes >> 4;
@@ -667,10 +702,18 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         while (threads > 32 && (1u << m) < (unsigned)threads) threads >>= 1;
         kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     } else {
-        auto kern = tile_kernel_pipe<R, Prog>;
+        constexpr int MSTD = sizeof(C) == 8 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
+        constexpr int LSTD = sizeof(C) == 8 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
+        const bool fast_ok = P.L == LSTD && tune_int("QCS_PIPE_GENERIC", 0) == 0;
+        void (*kern)(const Prog) = tile_kernel_pipe<R, Prog, 0>;
+        if (fast_ok && m == MSTD) kern = tile_kernel_pipe<R, Prog, MSTD>;
+        else if (fast_ok && m == MSTD + 1) kern = tile_kernel_pipe<R, Prog, MSTD + 1>;
+        const bool is_fast = kern != (void (*)(const Prog))tile_kernel_pipe<R, Prog, 0>;
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
             attr_done = true;
         }
         const size_t stage_bytes = PaddedLayout<C>::bytes(m);
@@ -690,7 +733,8 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         if (grid > P.ntiles) grid = P.ntiles;
         if (grid > MAX_GRID) grid = MAX_GRID;
         int threads = TILE_THREADS;
-        while (threads > 32 && (1u << m) < (unsigned)threads * 2u) threads >>= 1;
+        if (!is_fast)
+            while (threads > 32 && (1u << m) < (unsigned)threads * 2u) threads >>= 1;
         kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     }
     return cudaGetLastError() == cudaSuccess ? QCS_OK : set_error(QCS_ERR_CUDA, "tile kernel launch failed");

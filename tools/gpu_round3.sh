@@ -18,7 +18,7 @@ timeout 300 python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_kernel -c 18 -o /tmp/prof python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu exit $?" | tee -a gpurun_out/summary.txt
 ncu -i /tmp/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
-ncu -i /tmp/prof.ncu-rep --page source --csv --kernel-id :::10 > gpurun_out/prof_source_k10.csv 2>/dev/null
+ncu -i /tmp/prof.ncu-rep --page source --csv --kernel-name regex:260 --launch-count 1 > gpurun_out/prof_source_fused.csv 2>gpurun_out/prof_source_fused.err
 ncu -i /tmp/prof.ncu-rep --page source --csv --kernel-id :::1 > gpurun_out/prof_source_k1.csv 2>/dev/null
 cat gpurun_out/summary.txt
 for f in gpurun_out/pytest_pipe.log gpurun_out/pytest_bulk.log gpurun_out/smoke.log; do echo "== $f"; tail -n 8 $f; done
