@@ -33,63 +33,7 @@ sys.path.insert(0, ROOT)
 SEED = 1234
 
 
-def measured_peak():
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    try:
-        with open(path) as f:
-            return float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (of measured)'
-    except Exception:
-        return 6650.0, 'B200_PROFILING.md fallback 6.65 TB/s (of fallback)'
-
-
-def recorded_traffic(tag):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            return json.load(f).get(tag)
-    except Exception:
-        return None
-
-
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
-        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-        return self
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == 'Active'})
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+from qcircuits_b200.benchutil import ClockSampler, measured_peak, recorded_traffic  # noqa: E402
 
 
 def cpu_port_gates_per_s(orc, n_sample, n_target, budget_s, depth):

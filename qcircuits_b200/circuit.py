@@ -21,8 +21,8 @@ from .state import State
 class _Gate:
     __slots__ = ('plan', 'bits', 'nd_mask', 'd_mask', 'entries', 'wide', 'op')
 
-    def __init__(self, op, bits):
-        plan = op._plan()
+    def __init__(self, op, bits, plan=None):
+        plan = op._plan() if plan is None else plan
         self.op, self.plan, self.bits = op, plan, bits
         tmask = 0
         for q in plan.targets:
@@ -36,6 +36,75 @@ class _Gate:
         t = len(plan.targets)
         self.entries = (1 << t) if plan.diagonal else (1 << (2 * t))
         self.wide = t > _lib.QCS_MAX_OP_QUBITS
+
+
+def tile_limits(dtype):
+    """(low_bits, tile_bits) of the tile engine for this amplitude dtype (qcs_tile_limits)."""
+    low, tile = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.load().qcs_tile_limits(_lib.dtype_code(dtype), ctypes.byref(low), ctypes.byref(tile)))
+    return low.value, tile.value
+
+
+def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512):
+    """Greedy fusion: repeatedly pick the tile (low bits + a window of high bits) that admits the most
+    pending gates, where a gate may overtake an earlier one only if they commute (they share no bit on
+    which either acts non-diagonally).  ``gates`` are records with nd_mask / d_mask / entries / wide over
+    the n flat bits of the (local) state.  Returns lists of indices into ``gates``."""
+    low, tile = tile_limits(dtype)
+    L = min(low, n)
+    hcap = max(0, min(tile - low, n - L))
+    low_mask = (1 << L) - 1
+    pool_cap = 12288 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
+    max_ops = min(max_ops, _lib.QCS_MAX_OPS)
+    remaining = list(range(len(gates)))
+    passes = []
+    full = (1 << n) - 1
+
+    def scan(tile_mask):
+        blk_nd = blk_d = 0
+        taken, entries = [], 0
+        for idx in remaining[:lookahead]:
+            g = gates[idx]
+            ok = (not g.wide and (g.nd_mask & ~tile_mask) == 0 and (g.nd_mask & (blk_nd | blk_d)) == 0
+                  and (g.d_mask & blk_nd) == 0 and len(taken) < max_ops and entries + g.entries <= pool_cap)
+            if ok:
+                taken.append(idx)
+                entries += g.entries
+            else:
+                blk_nd |= g.nd_mask
+                blk_d |= g.d_mask
+                if blk_nd == full:
+                    break
+        return taken
+
+    while remaining:
+        first = gates[remaining[0]]
+        if first.wide:                      # operator wider than the tile engine: its own dense pass
+            passes.append([remaining.pop(0)])
+            continue
+        candidates = [low_mask]
+        for s in range(L, n - hcap + 1):
+            candidates.append(low_mask | (((1 << hcap) - 1) << s))
+        # the first pending gate must always be schedulable: its own high bits, padded upwards
+        need = first.nd_mask & ~low_mask
+        if need and bin(need).count('1') <= hcap:
+            m, b = need, L
+            while bin(m).count('1') < hcap and b < n:
+                m |= 1 << b
+                b += 1
+            candidates.append(low_mask | m)
+        best = None
+        for mask in candidates:
+            taken = scan(mask)
+            if best is None or len(taken) > len(best):
+                best = taken
+        if not best:
+            # a gate whose dense targets exceed the preferred tile even alone: libqcs shrinks the low run
+            best = [remaining[0]]
+        passes.append(best)
+        chosen = set(best)
+        remaining = [i for i in remaining if i not in chosen]
+    return passes
 
 
 class Circuit:
@@ -65,70 +134,9 @@ class Circuit:
     def schedule(self, dtype=np.complex128, fuse=True, max_ops=24, lookahead=512):
         """Group the gates into passes.  Returns a list of lists of gate indices (execution order
         inside a pass = list order).  ``fuse=False`` gives one pass per gate."""
-        n = self.n
         if not fuse:
             return [[i] for i in range(len(self.gates))]
-        low, tile = ctypes.c_int(), ctypes.c_int()
-        _lib.check(_lib.load().qcs_tile_limits(_lib.dtype_code(dtype), ctypes.byref(low), ctypes.byref(tile)))
-        L = min(low.value, n)
-        hcap = max(0, min(tile.value - low.value, n - L))
-        low_mask = (1 << L) - 1
-        pool_cap = 12288 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
-        max_ops = min(max_ops, _lib.QCS_MAX_OPS)
-        gates = self.gates
-        remaining = list(range(len(gates)))
-        passes = []
-
-        def scan(tile_mask, commit):
-            blk_nd = blk_d = 0
-            taken, entries = [], 0
-            full = (1 << n) - 1
-            for idx in remaining[:lookahead]:
-                g = gates[idx]
-                ok = (not g.wide and (g.nd_mask & ~tile_mask) == 0 and (g.nd_mask & (blk_nd | blk_d)) == 0
-                      and (g.d_mask & blk_nd) == 0 and len(taken) < max_ops and entries + g.entries <= pool_cap)
-                if ok:
-                    taken.append(idx)
-                    entries += g.entries
-                else:
-                    blk_nd |= g.nd_mask
-                    blk_d |= g.d_mask
-                    if blk_nd == full:
-                        break
-            return taken
-
-        while remaining:
-            first = gates[remaining[0]]
-            if first.wide:                      # operator wider than the tile engine: its own dense pass
-                passes.append([remaining.pop(0)])
-                continue
-            candidates = [low_mask]
-            for s in range(L, n - hcap + 1):
-                candidates.append(low_mask | (((1 << hcap) - 1) << s))
-            # the first pending gate must always be schedulable: its own high bits, padded upwards
-            need = first.nd_mask & ~low_mask
-            if need:
-                m, b = need, L
-                while bin(m).count('1') < hcap and b < n:
-                    m |= 1 << b
-                    b += 1
-                if bin(need).count('1') <= hcap:
-                    while bin(m).count('1') > hcap:
-                        extra = (m & ~need)
-                        m &= ~(extra & -extra)
-                    candidates.append(low_mask | m)
-            best, best_mask = None, None
-            for mask in candidates:
-                taken = scan(mask, False)
-                if best is None or len(taken) > len(best):
-                    best, best_mask = taken, mask
-            if not best:
-                # a gate whose dense targets exceed one tile even alone: give it the tile it needs
-                best = [remaining[0]]
-            passes.append(best)
-            chosen = set(best)
-            remaining = [i for i in remaining if i not in chosen]
-        return passes
+        return schedule_passes(self.gates, self.n, dtype, max_ops=max_ops, lookahead=lookahead)
 
     def _compiled(self, dtype, fuse, max_ops):
         key = (np.dtype(dtype).str, fuse, max_ops)

@@ -1,0 +1,318 @@
+"""Sharded states: one process per GPU, the state split on its top log2(P) flat bits (north_star (4),
+SURVEY.md 8e).
+
+A state of n qubits over P = 2^g ranks: rank r owns the contiguous block of 2^(n-g) amplitudes whose
+top g physical bits equal r.  Which *logical* qubit sits on which *physical* bit is tracked by
+``ShardedState.phys`` (qubit -> physical bit), so that
+
+* a gate whose non-diagonal targets are all on local physical bits runs with no communication, through
+  the same fused tile passes as on one GPU.  Control bits and diagonal targets on rank bits become
+  per-rank constants (``specialize``): the op is dropped, loses the control, or turns into a phase;
+* when the next gates need a qubit that sits on a rank bit, the g rank bits are exchanged with the top g
+  local bits by ONE NCCL all-to-all over NVLink (``torch.distributed.all_to_all_single`` on contiguous
+  2^(n-2g)-amplitude blocks: no pack/unpack kernel), and only the map changes;
+* the norm is reduced across ranks once, at the end (linear ops commute with the scalar).
+
+``dist_schedule`` is pure host logic and is the same on every rank; it is exercised on CPU (gloo,
+world_size 2) in tests/test_dist_cpu.py with a NumPy engine standing in for the kernels.
+"""
+import numpy as np
+
+from . import _lib
+from ._gates import GatePlan
+from .circuit import _Gate, schedule_passes
+
+
+# ---------------------------------------------------------------------------------------------------
+# host logic
+# ---------------------------------------------------------------------------------------------------
+def initial_layout(n, g):
+    """qubit -> physical bit.  Qubits 0..g-1 start on the rank bits (canonical: bit n-1-q).  The top g
+    LOCAL bits -- the ones that are traded away by the first exchange -- get the qubits from the far end
+    of the register, so that the two sets that alternate on the rank bits block as little of the circuit
+    as possible; everything else keeps its order."""
+    n_local = n - g
+    phys = [None] * n
+    for q in range(g):
+        phys[q] = n - 1 - q
+    far = list(range(n - g, n)) if n - g >= g else []
+    for i, q in enumerate(far):
+        phys[q] = n_local - 1 - i
+    free_bits = [b for b in range(n_local - 1, -1, -1) if b not in set(p for p in phys if p is not None)]
+    rest = [q for q in range(n) if phys[q] is None]
+    for q, b in zip(rest, free_bits):
+        phys[q] = b
+    return phys
+
+
+def canonical_layout(n):
+    return [n - 1 - q for q in range(n)]
+
+
+def dist_schedule(gates, n, g, phys=None):
+    """Split a gate list into steps that need no communication and exchanges.
+
+    ``gates``: records with ``plan`` (GatePlan) and ``qubits`` (logical qubit of each operator qubit).
+    Returns (steps, final_phys); a step is ('local', [(gate index, [physical bit per operator qubit])]),
+    ('swap',) -- trade the g rank bits with the top g local bits -- or ('lperm', src_bit) -- a local bit
+    permutation (dst bit b takes src bit src_bit[b]), only needed when one gate has non-diagonal targets
+    in both halves of an exchange."""
+    n_local = n - g
+    phys = list(initial_layout(n, g) if phys is None else phys)
+    steps = []
+    pending = list(range(len(gates)))
+    qmask = []
+    for gate in gates:
+        plan = gate.plan
+        nd = 0 if plan.diagonal else sum(1 << gate.qubits[t] for t in plan.targets)
+        d = sum(1 << gate.qubits[c] for c in plan.controls)
+        if plan.diagonal:
+            d |= sum(1 << gate.qubits[t] for t in plan.targets)
+        qmask.append((nd, d))
+    stuck = 0
+    while pending:
+        blk_nd = blk_d = 0
+        now, rest = [], []
+        for idx in pending:
+            nd, d = qmask[idx]
+            local = all(phys[q] < n_local for q in range(n) if (nd >> q) & 1)
+            if local and (nd & (blk_nd | blk_d)) == 0 and (d & blk_nd) == 0:
+                now.append((idx, [phys[q] for q in gates[idx].qubits]))
+            else:
+                rest.append(idx)
+                blk_nd |= nd
+                blk_d |= d
+        if now:
+            steps.append(('local', now))
+            stuck = 0
+        pending = rest
+        if not pending:
+            break
+        if g == 0:
+            raise RuntimeError('unschedulable gate on a single shard')
+        stuck += 1
+        if stuck >= 2:
+            # the first pending gate has non-diagonal targets on both sides of the exchange: move its
+            # local targets out of the top g local bits first
+            nd, _ = qmask[pending[0]]
+            need_local = [q for q in range(n) if (nd >> q) & 1 and phys[q] < n_local]
+            top = set(range(n_local - g, n_local))
+            movers = [q for q in need_local if phys[q] in top]
+            safe = [b for b in range(n_local - g) if all(phys[q] != b or not ((nd >> q) & 1) for q in range(n))]
+            if len(movers) > len(safe):
+                raise RuntimeError('gate too wide for this sharding')
+            src_bit = list(range(n_local))
+            qubit_at = {phys[q]: q for q in range(n)}
+            for q, b in zip(movers, safe):
+                a = phys[q]
+                other = qubit_at[b]
+                src_bit[a], src_bit[b] = src_bit[b], src_bit[a]
+                phys[q], phys[other] = b, a
+                qubit_at[b], qubit_at[a] = q, other
+            if movers:
+                steps.append(('lperm', src_bit))
+            elif stuck >= 4:
+                raise RuntimeError('scheduler made no progress')
+        steps.append(('swap',))
+        qubit_at = {phys[q]: q for q in range(n)}
+        for i in range(g):
+            qa, qb = qubit_at[n_local + i], qubit_at[n_local - g + i]
+            phys[qa], phys[qb] = n_local - g + i, n_local + i
+    return steps, phys
+
+
+def specialize(plan, bits, n_local, rank):
+    """A gate as seen by one rank: controls / diagonal targets on rank bits are resolved with the rank's
+    bit values.  Returns None (identity on this rank) or (GatePlan, local bits per operator qubit)."""
+    def rank_bit(p):
+        return (rank >> (p - n_local)) & 1
+
+    controls = []
+    for c in plan.controls:
+        if bits[c] >= n_local:
+            if not rank_bit(bits[c]):
+                return None
+        else:
+            controls.append(c)
+    targets = list(plan.targets)
+    matrix = plan.matrix
+    if plan.diagonal:
+        diag = np.asarray(matrix).reshape([2] * len(targets))
+        keep = []
+        index = []
+        for t in targets:
+            if bits[t] >= n_local:
+                index.append(rank_bit(bits[t]))
+            else:
+                index.append(slice(None))
+                keep.append(t)
+        diag = np.ascontiguousarray(diag[tuple(index)]).reshape(-1)
+        targets = keep
+        if not targets:
+            # a pure phase on this rank (conditioned on the remaining local controls, if any)
+            phase = complex(diag[0])
+            if controls:
+                t = controls.pop()
+                targets, diag = [t], np.array([1.0, phase], dtype=np.complex128)
+            else:
+                if phase == 1.0:
+                    return None
+                any_bit = 0
+                new_plan = GatePlan(1, [], [0], True, np.array([phase, phase], dtype=np.complex128), None)
+                return new_plan, [any_bit]
+        matrix = diag
+    else:
+        if any(bits[t] >= n_local for t in targets):
+            raise ValueError('non-diagonal target on a rank bit')
+    # renumber operator qubits compactly
+    used = controls + targets
+    remap = {q: i for i, q in enumerate(used)}
+    new_plan = GatePlan(len(used), [remap[c] for c in controls], [remap[t] for t in targets], plan.diagonal,
+                        np.ascontiguousarray(matrix), None)
+    return new_plan, [bits[q] for q in used]
+
+
+class _LogicalGate:
+    __slots__ = ('plan', 'qubits')
+
+    def __init__(self, plan, qubits):
+        self.plan, self.qubits = plan, list(qubits)
+
+
+# ---------------------------------------------------------------------------------------------------
+# engines: what a rank does to its shard (CUDA in the product; tests plug in a NumPy checker)
+# ---------------------------------------------------------------------------------------------------
+class CudaEngine:
+    """Shard + spare buffer on the current CUDA device; passes run through libqcs."""
+
+    def __init__(self, n_local, dtype):
+        self.n_local, self.dtype = n_local, np.dtype(dtype)
+        self.buf = _lib.alloc_amplitudes(n_local, dtype)
+        self.spare = _lib.alloc_amplitudes(n_local, dtype)
+        self.code = _lib.dtype_code(dtype)
+        self.launches = 0
+
+    def set_basis(self, index):
+        lib = _lib.load()
+        if index is None:
+            self.buf.zero_()
+        else:
+            _lib.check(lib.qcs_set_basis(self.buf.data_ptr(), self.n_local, self.code, index, _lib.stream_ptr()))
+
+    def run_local(self, rank_gates, max_ops):
+        from ._device import make_ops
+        lib = _lib.load()
+        ws = _lib.workspace().data_ptr()
+        for group in schedule_passes(rank_gates, self.n_local, self.dtype, max_ops=max_ops):
+            ops, keep = make_ops([(rank_gates[i].plan, rank_gates[i].bits, False) for i in group])
+            _lib.check(lib.qcs_apply_fused(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, ops,
+                                           len(ops), None, None, ws, _lib.stream_ptr()))
+            self.launches += 1
+
+    def permute(self, src_bit):
+        _lib.check(_lib.load().qcs_permute_bits(self.spare.data_ptr(), self.buf.data_ptr(), self.n_local, self.code,
+                                               _lib.int32_array(src_bit), _lib.stream_ptr()))
+        self.buf, self.spare = self.spare, self.buf
+        self.launches += 1
+
+    def exchange(self, group=None):
+        import torch.distributed as dist
+        dist.all_to_all_single(self.spare, self.buf, group=group)
+        self.buf, self.spare = self.spare, self.buf
+
+    def norm2(self):
+        out = _lib.alloc_scalar()
+        _lib.check(_lib.load().qcs_abs2(None, self.buf.data_ptr(), self.n_local, self.code, None, out.data_ptr(),
+                                        _lib.workspace().data_ptr(), _lib.stream_ptr()))
+        return out[:1]
+
+    def marginals(self, bitpos):
+        t = _lib.torch()
+        out = t.empty(1 << len(bitpos), dtype=t.float64, device='cuda')
+        ws = _lib.workspace()
+        _lib.check(_lib.load().qcs_marginal_probs(out.data_ptr(), self.buf.data_ptr(), self.n_local, self.code,
+                                                  _lib.int32_array(bitpos), len(bitpos), None, ws.data_ptr(),
+                                                  ws.numel(), _lib.stream_ptr()))
+        return out
+
+
+class ShardedState:
+    """This rank's part of an n-qubit state spread over ``world`` = 2^g ranks."""
+
+    def __init__(self, n, dtype=np.complex64, rank=None, world=None, engine=None, group=None):
+        import torch.distributed as dist
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.g = int(round(np.log2(self.world)))
+        if 2 ** self.g != self.world:
+            raise ValueError('the number of ranks must be a power of two')
+        self.n, self.n_local, self.dtype, self.group = n, n - self.g, np.dtype(dtype), group
+        if self.n_local < 2 * self.g:
+            raise ValueError('state too small to shard over this many ranks')
+        self.engine = CudaEngine(self.n_local, dtype) if engine is None else engine
+        self.phys = canonical_layout(n)
+        self.norm = None
+        self.exchanges = 0
+
+    def set_zeros(self, layout=None):
+        """|0...0>: index 0 lives on rank 0 under any layout."""
+        self.phys = list(initial_layout(self.n, self.g) if layout is None else layout)
+        self.engine.set_basis(0 if self.rank == 0 else None)
+        self.norm = None
+        return self
+
+    def run(self, circuit, max_ops=24):
+        """Apply a Circuit (its gates are on logical qubits).  Collective: every rank calls it."""
+        gates = [_LogicalGate(gt.plan, [circuit.n - 1 - b for b in gt.bits]) for gt in circuit.gates]
+        steps, phys = dist_schedule(gates, self.n, self.g, self.phys)
+        for step in steps:
+            if step[0] == 'local':
+                rank_gates = []
+                for idx, bits in step[1]:
+                    sp = specialize(gates[idx].plan, bits, self.n_local, self.rank)
+                    if sp is not None:
+                        rank_gates.append(_Gate(None, sp[1], plan=sp[0]))
+                if rank_gates:
+                    self.engine.run_local(rank_gates, max_ops)
+            elif step[0] == 'lperm':
+                self.engine.permute(step[1])
+            else:
+                self.engine.exchange(self.group)
+                self.exchanges += 1
+        self.phys = phys
+        self.norm = None
+        return self
+
+    def norm2(self):
+        """Squared norm of the whole state (all-reduce of the per-rank sums)."""
+        import torch.distributed as dist
+        part = self.engine.norm2()
+        dist.all_reduce(part, group=self.group)
+        return float(part[0].item())
+
+    def marginals(self, qubits):
+        """Marginal distribution of the listed logical qubits (first = MSB), normalised; all ranks get it."""
+        import torch.distributed as dist
+        t = _lib.torch()
+        m = len(qubits)
+        pos = [self.phys[q] for q in qubits]
+        local = [(j, p) for j, p in enumerate(pos) if p < self.n_local]
+        if local:
+            part = self.engine.marginals([p for _, p in local])
+        else:
+            part = self.engine.norm2().reshape(1)
+        full = t.zeros(1 << m, dtype=t.float64, device=part.device)
+        idx = np.zeros(1 << len(local), dtype=np.int64)
+        for x in range(1 << len(local)):
+            o = 0
+            for k, (j, _) in enumerate(local):
+                if (x >> (len(local) - 1 - k)) & 1:
+                    o |= 1 << (m - 1 - j)
+            for j, p in enumerate(pos):
+                if p >= self.n_local and (self.rank >> (p - self.n_local)) & 1:
+                    o |= 1 << (m - 1 - j)
+            idx[x] = o
+        full[t.from_numpy(idx).to(part.device)] = part
+        dist.all_reduce(full, group=self.group)
+        out = full.cpu().numpy()
+        return out / out.sum()

@@ -1,0 +1,150 @@
+"""bench.py body for N > 1 (launched by torchrun, one rank per GPU): the sharded layered circuit.
+
+Weak scaling: every rank holds 2^33 complex64 amplitudes (64 GiB) -- 34 qubits on 2 GPUs, 35 on 4,
+36 on 8 (BASELINE.json: "36q at 8 GPUs"; 36 qubits do not fit 2 or 4 B200s).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+SEED = 1234
+
+
+def main(args):
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .dist import ShardedState, dist_schedule, _LogicalGate
+    from .workloads import layered_circuit
+    from .benchutil import ClockSampler, measured_peak
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', str(rank)))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    n, depth = args.qubits, args.depth
+    g = int(np.log2(world))
+    np_dtype = np.complex64 if args.dtype == 'c64' else np.complex128
+    amp_bytes = 8 if args.dtype == 'c64' else 16
+    circ = layered_circuit(n, depth, seed=SEED)
+    ngates = len(circ)
+    st = ShardedState(n, np_dtype)
+    shard_bytes = (2 ** st.n_local) * amp_bytes
+
+    def step():
+        st.set_zeros()
+        st.run(circ, max_ops=args.max_ops)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    total = st.norm2()
+    launches0, exch0 = st.engine.launches, st.exchanges
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    passes = (st.engine.launches - launches0) / args.steps
+    exchanges = (st.exchanges - exch0) / args.steps
+    marg = st.marginals([0, n // 2, n - 1])
+
+    # exchange alone, timed on the device (max over ranks)
+    torch.cuda.synchronize()
+    dist.barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    st.engine.exchange(None)
+    st.engine.exchange(None)
+    x1.record()
+    torch.cuda.synchronize()
+    xms = torch.tensor([x0.elapsed_time(x1) / 2], dtype=torch.float64, device='cuda')
+    dist.all_reduce(xms, op=dist.ReduceOp.MAX)
+    exchange_ms = float(xms.item())
+
+    # end to end: each rank's shard starts in pinned host memory and the result returns to pinned host memory.
+    # Only when the box has ample RAM (two pinned shards per rank): a host OOM would take the whole box down.
+    e2e = None
+    if not args.skip_e2e:
+        from .dist import initial_layout
+        try:
+            import psutil
+            need = 2.0 * shard_bytes * world
+            ok = torch.tensor([1 if psutil.virtual_memory().available > 3.0 * need else 0], device='cuda')
+        except Exception:
+            ok = torch.tensor([0], device='cuda')
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()):
+            host_in = torch.zeros(st.engine.buf.numel(), dtype=st.engine.buf.dtype).pin_memory()
+            host_out = torch.empty(st.engine.buf.numel(), dtype=st.engine.buf.dtype).pin_memory()
+            if rank == 0:
+                host_in[0] = 1.0
+
+            def e2e_step():
+                st.phys = list(initial_layout(n, g))
+                st.engine.buf.copy_(host_in, non_blocking=True)
+                st.run(circ, max_ops=args.max_ops)
+                host_out.copy_(st.engine.buf, non_blocking=True)
+
+            e2e_step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            reps = max(1, args.steps // 2)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(reps):
+                e2e_step()
+            t1.record()
+            torch.cuda.synchronize()
+            tms = torch.tensor([t0.elapsed_time(t1) / reps], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            e2e = {'value': ngates / (float(tms.item()) * 1e-3), 'unit': 'gates/s', 'ms_per_step': float(tms.item()),
+                   'h2d_bytes_per_step': int(shard_bytes * world), 'd2h_bytes_per_step': int(shard_bytes * world)}
+            del host_in, host_out
+        else:
+            e2e = {'value': None, 'unit': 'gates/s', 'skipped': 'host RAM too small to pin two shards per rank safely',
+                   'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nvlink = 770.0   # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
+        pass_bytes = 2.0 * shard_bytes
+        sent = shard_bytes * (1.0 - 1.0 / world)
+        t_roof = (passes * pass_bytes / (peak * 1e9) + exchanges * sent / (nvlink * 1e9)) * 1e3
+        achieved = pass_bytes * passes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            'metric': 'gates/s, random layered circuit', 'value': ngates / (ms_per_step * 1e-3), 'unit': 'gates/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+            'data': 'synthetic',
+            'config': {'workload': 'layered H/RX/RZ+CNOT/CZ circuit, %d qubits, depth %d, seed %d, |0..0> input, sharded '
+                                   'on the top %d bits' % (n, depth, SEED, g),
+                       'gates': ngates, 'shard_gib': shard_bytes / 2 ** 30, 'passes_per_step_rank0': passes,
+                       'exchanges_per_step': exchanges, 'max_ops_per_pass': args.max_ops,
+                       'l2': 'shard (%.0f GiB) is far larger than L2; no flush needed' % (shard_bytes / 2 ** 30)},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src, 'kernel': 'qcs::tile_kernel_pipe (fused gate pass), per GPU',
+                         'bytes_per_launch': pass_bytes,
+                         'combined': {'hbm_plus_nvlink_roofline_ms': t_roof, 'measured_ms': ms_per_step,
+                                      'frac': t_roof / ms_per_step, 'nvlink_gbs_per_dir': nvlink,
+                                      'exchange_ms_measured': exchange_ms,
+                                      'exchange_gbs_per_gpu': sent / (exchange_ms * 1e-3) / 1e9}},
+            'cpu_baseline': None,
+            'e2e': e2e, 'clocks': clocks.summary(),
+            'gpu_launches': int(passes * args.steps),
+            'norm_check': total, 'marginals_q0_mid_last': [float(x) for x in marg],
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
