@@ -88,7 +88,7 @@ def main():
     ap.add_argument('--qubits', type=int, default=None)
     ap.add_argument('--depth', type=int, default=40)
     ap.add_argument('--dtype', default='c64', choices=['c64', 'c128'])
-    ap.add_argument('--max-ops', type=int, default=24)
+    ap.add_argument('--max-ops', type=int, default=16)
     ap.add_argument('--no-fuse', action='store_true')
     ap.add_argument('--cpu-qubits', type=int, default=24)
     ap.add_argument('--cpu-budget', type=float, default=12.0)
@@ -137,6 +137,28 @@ def main():
     pass_bytes = 2.0 * (2 ** n) * amp_bytes
     achieved = pass_bytes * passes / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = measured_peak()
+    # the per-gate path (Operator.__call__: one pass per gate, north_star "per gate pass"): the first two
+    # layers of the same circuit, unfused, timed the same way
+    from qcircuits_b200.workloads import layered_gate_list, operator_for
+    from qcircuits_b200.circuit import Circuit
+    two_layers = Circuit(n)
+    for name, theta, qs in layered_gate_list(n, 2, seed=SEED):
+        two_layers.append(operator_for(name, theta), list(qs))
+    for _ in range(2):
+        two_layers.run(state0, fuse=False)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(3):
+        two_layers.run(state0, fuse=False)
+    g1.record()
+    torch.cuda.synchronize()
+    gate_ms = g0.elapsed_time(g1) / (3 * len(two_layers))
+    per_gate = {'bound': 'hbm', 'achieved': pass_bytes / (gate_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'frac': pass_bytes / (gate_ms * 1e-3) / 1e9 / peak, 'ms_per_launch': gate_ms,
+                'gates_per_s': 1e3 / gate_ms, 'launches_timed': 3 * len(two_layers),
+                'frac_of_8TBs_nominal': pass_bytes / (gate_ms * 1e-3) / 1e9 / 8000.0,
+                'what': 'one tile-kernel pass per gate (first two layers of the circuit, unfused)'}
     # sanity: unit norm after 1780 gates
     probs_sum = float(out._dv.norm2()[0].item()) / float(out._dv.norm[0].item())
 
@@ -182,6 +204,7 @@ def main():
                      'traffic': recorded_traffic('tile_%s_%dq' % (args.dtype, n)), 'peak_source': peak_src,
                      'kernel': 'qcs::tile_kernel (fused gate pass)', 'bytes_per_launch': pass_bytes,
                      'ms_per_launch': ms_per_step / passes, 'frac_of_8TBs_nominal': achieved / 8000.0},
+        'roofline_per_gate_pass': per_gate,
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': passes * args.steps,
         'clocks': clocks.summary(), 'step_ms': step_ms, 'norm_check': probs_sum,
     }

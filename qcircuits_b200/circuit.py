@@ -107,6 +107,46 @@ def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512):
     return passes
 
 
+def merge_single_qubit_gates(gates):
+    """Peephole fusion before scheduling: an uncontrolled one-qubit gate waits in a per-bit accumulator;
+    later one-qubit gates on the same bit multiply into it, gates that act *diagonally* on the bit
+    (controls, diagonal targets) are let through while the accumulator is itself diagonal (they commute),
+    and anything else flushes it.  So RZ / S / T slide through CZ and CNOT controls into the next H or RX
+    and disappear as separate ops.  Returns a new gate list (same unitary up to rounding)."""
+    from . import _gates
+    out = []
+    acc = {}          # bit -> 2x2 matrix
+
+    def flush(b):
+        M = acc.pop(b, None)
+        if M is None:
+            return
+        if np.array_equal(M, np.eye(2)):
+            return
+        out.append(_Gate(None, [b], plan=_gates.analyze(M)))
+
+    for g in gates:
+        plan = g.plan
+        if not g.wide and len(plan.targets) == 1 and not plan.controls:
+            b = g.bits[plan.targets[0]]
+            M = np.diag(plan.matrix) if plan.diagonal else plan.matrix
+            acc[b] = M @ acc[b] if b in acc else np.array(M, dtype=np.complex128)
+            continue
+        nd = g.nd_mask
+        for b in list(acc):
+            bit = 1 << b
+            if nd & bit:
+                flush(b)
+            elif g.d_mask & bit:
+                M = acc[b]
+                if M[0, 1] != 0 or M[1, 0] != 0:
+                    flush(b)
+        out.append(g)
+    for b in sorted(acc):
+        flush(b)
+    return out
+
+
 class Circuit:
     """An ordered list of gates on ``n`` qubits.
 
@@ -143,12 +183,15 @@ class Circuit:
         comp = self._plans.get(key)
         if comp is None:
             comp = []
-            for group in self.schedule(dtype, fuse=fuse, max_ops=max_ops):
-                g0 = self.gates[group[0]]
+            gates = merge_single_qubit_gates(self.gates) if fuse else self.gates
+            groups = (schedule_passes(gates, self.n, dtype, max_ops=max_ops) if fuse
+                      else [[i] for i in range(len(gates))])
+            for group in groups:
+                g0 = gates[group[0]]
                 if g0.wide:
                     comp.append(('dense', g0))
                 else:
-                    ops, keep = make_ops([(self.gates[i].plan, self.gates[i].bits, False) for i in group])
+                    ops, keep = make_ops([(gates[i].plan, gates[i].bits, False) for i in group])
                     comp.append(('tile', ops, keep, len(group)))
             self._plans[key] = comp
         return comp

@@ -68,3 +68,27 @@ def test_headline_circuit_fuses_well():
     assert len(passes) < 500
     unfused = c.schedule(np.complex64, fuse=False)
     assert len(unfused) == 1780
+
+
+def test_single_qubit_merge_preserves_the_unitary():
+    from qcircuits_b200.circuit import merge_single_qubit_gates
+    rng = np.random.default_rng(8)
+    n = 10
+    c = _layered(n, 8)
+    c.append(qc.PiBy8(), [3])
+    c.append(qc.Phase(), [3])
+    c.append(qc.Toffoli(), [3, 4, 5])
+    c.append(qc.Hadamard(), [3])
+    c.append(qc.Hadamard(), [3])          # H H = identity: dropped
+    c.append(qc.Operator.from_matrix(rand_unitary(rng, 3)), [1, 3, 8])
+    merged = merge_single_qubit_gates(c.gates)
+    assert len(merged) < 0.85 * len(c.gates)
+    vec = rand_state_vec(rng, n)
+    want = vec
+    for g in c.gates:
+        want = orc.apply_matrix_flat(g.plan.full, want, g.bits, renorm=False)
+    got = vec
+    for g in merged:
+        if g.plan.full is not None:
+            got = orc.apply_matrix_flat(g.plan.full, got, g.bits, renorm=False)
+    assert np.max(np.abs(got - want)) < 1e-12
