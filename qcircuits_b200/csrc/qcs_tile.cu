@@ -445,8 +445,8 @@ __device__ __forceinline__ void vec_norm_acc(double &acc, const uint4 v, double)
 // MT > 0: compile-time geometry -- the tile has MT bits, its low LSTD bits are contiguous, the CTA has
 // TILE_THREADS threads; every staging loop has a constant trip count.  MT == 0: everything at run time
 // (small states, unusual tiles).
-template <typename R, typename Prog, int MT>
-__global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel_pipe(const __grid_constant__ Prog P) {
+template <typename R, typename Prog, int MT, int OCC>
+__global__ void __launch_bounds__(TILE_THREADS, OCC) tile_kernel_pipe(const __grid_constant__ Prog P) {
     using C = typename CxT<R>::T;
     using Layout = PaddedLayout<C>;
     constexpr bool FAST = MT > 0;
@@ -705,23 +705,34 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         constexpr int MSTD = sizeof(C) == 8 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
         constexpr int LSTD = sizeof(C) == 8 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
         const bool fast_ok = P.L == LSTD && tune_int("QCS_PIPE_GENERIC", 0) == 0;
-        void (*kern)(const Prog) = tile_kernel_pipe<R, Prog, 0>;
-        if (fast_ok && m == MSTD) kern = tile_kernel_pipe<R, Prog, MSTD>;
-        else if (fast_ok && m == MSTD + 1) kern = tile_kernel_pipe<R, Prog, MSTD + 1>;
-        const bool is_fast = kern != (void (*)(const Prog))tile_kernel_pipe<R, Prog, 0>;
+        int ctas = tune_int("QCS_PIPE_CTAS", 2);
+        if (ctas < 1) ctas = 1;
+        if (ctas > 3) ctas = 3;
+        const bool fast12 = fast_ok && m == MSTD, fast13 = fast_ok && m == MSTD + 1;
+        if (!(fast12 || fast13) && ctas > 2) ctas = 2;
+        void (*kern)(const Prog) = tile_kernel_pipe<R, Prog, 0, 2>;
+        if (fast12) kern = ctas == 3 ? tile_kernel_pipe<R, Prog, MSTD, 3> : tile_kernel_pipe<R, Prog, MSTD, 2>;
+        else if (fast13) kern = ctas == 3 ? tile_kernel_pipe<R, Prog, MSTD + 1, 3> : tile_kernel_pipe<R, Prog, MSTD + 1, 2>;
+        const bool is_fast = fast12 || fast13;
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
-            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
-            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
+            const int lim = (int)TILE_SMEM_BUDGET;
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             attr_done = true;
         }
         const size_t stage_bytes = PaddedLayout<C>::bytes(m);
-        int ctas = tune_int("QCS_PIPE_CTAS", 2);
-        if (ctas < 1) ctas = 1;
-        if (ctas > 2) ctas = 2;
-        int S = (int)((TILE_SMEM_BUDGET / ctas - prog - 1024) / stage_bytes);
-        while (S < 2 && ctas > 1) { --ctas; S = (int)((TILE_SMEM_BUDGET / ctas - prog - 1024) / stage_bytes); }
+        const size_t sm_smem = 227 * 1024;      // opt-in shared memory per SM; each resident CTA reserves 1 KB
+        int S = (int)((sm_smem / ctas - prog - 1024) / stage_bytes);
+        while (S < 2 && ctas > 1) {
+            --ctas;
+            S = (int)((sm_smem / ctas - prog - 1024) / stage_bytes);
+            if (fast12) kern = tile_kernel_pipe<R, Prog, MSTD, 2>;
+            else if (fast13) kern = tile_kernel_pipe<R, Prog, MSTD + 1, 2>;
+        }
         S = S > TILE_MAX_STAGES ? TILE_MAX_STAGES : S;
         const int tuned = tune_int("QCS_PIPE_STAGES", S);
         if (tuned < S) S = tuned;
