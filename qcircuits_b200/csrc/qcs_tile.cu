@@ -103,63 +103,121 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 // ------------------------------------------------------------------------------------------------
 // register sweeps
 // ------------------------------------------------------------------------------------------------
-// One 2x2 gate on register bit J of the 2^RB amplitudes a thread holds.  FORM picks the arithmetic
-// (general complex / real matrix / real diagonal + imaginary off-diagonal / anti-diagonal / X swap),
-// CTRL adds the control predicates: (x & rc) == rv over the register bits (uniform across the CTA)
-// and tp (per thread).
-template <typename R, int NX, int J, int FORM, bool CTRL>
-__device__ __forceinline__ void u1_apply(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
-                                         uint32_t rc, uint32_t rv, bool tp) {
+// Register-op bodies.  Every position that selects registers (target bit J, register control bit CB,
+// phase bits) is a template parameter, so a body is straight-line arithmetic on named registers with no
+// per-amplitude predicate; the class id of an op (RegOp::code) picks the body through one jump table.
+// Controls that are not register bits are one per-thread predicate around the whole body.
+template <typename R, int FORM>
+__device__ __forceinline__ void butterfly(typename CxT<R>::T &a0, typename CxT<R>::T &a1, const typename CxT<R>::T m00,
+                                          const typename CxT<R>::T m01, const typename CxT<R>::T m10,
+                                          const typename CxT<R>::T m11) {
     using C = typename CxT<R>::T;
-    constexpr uint32_t BIT = 1u << J;
-    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
-#pragma unroll
-    for (uint32_t x0 = 0; x0 < NX; ++x0) {
-        if (x0 & BIT) continue;
-        const uint32_t x1 = x0 | BIT;
-        if (!CTRL || (((x0 & rc) == rv) && tp)) {
-            const C t0 = a[x0], t1 = a[x1];
-            C r0, r1;
-            if (FORM == U1_REAL) {
-                r0.x = fma(m00.x, t0.x, m01.x * t1.x); r0.y = fma(m00.x, t0.y, m01.x * t1.y);
-                r1.x = fma(m10.x, t0.x, m11.x * t1.x); r1.y = fma(m10.x, t0.y, m11.x * t1.y);
-            } else if (FORM == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
-                r0.x = fma(m00.x, t0.x, -m01.y * t1.y); r0.y = fma(m00.x, t0.y, m01.y * t1.x);
-                r1.x = fma(m11.x, t1.x, -m10.y * t0.y); r1.y = fma(m11.x, t1.y, m10.y * t0.x);
-            } else if (FORM == U1_ANTIDIAG) {
-                r0 = cmul(m01, t1);
-                r1 = cmul(m10, t0);
-            } else if (FORM == U1_SWAP) {
-                r0 = t1; r1 = t0;
-            } else {
-                r0 = cmul(m00, t0); cfma(r0, m01, t1);
-                r1 = cmul(m10, t0); cfma(r1, m11, t1);
-            }
-            a[x0] = r0; a[x1] = r1;
-        }
+    const C t0 = a0, t1 = a1;
+    C r0, r1;
+    if (FORM == U1_REAL) {
+        r0.x = fma(m00.x, t0.x, m01.x * t1.x); r0.y = fma(m00.x, t0.y, m01.x * t1.y);
+        r1.x = fma(m10.x, t0.x, m11.x * t1.x); r1.y = fma(m10.x, t0.y, m11.x * t1.y);
+    } else if (FORM == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
+        r0.x = fma(m00.x, t0.x, -m01.y * t1.y); r0.y = fma(m00.x, t0.y, m01.y * t1.x);
+        r1.x = fma(m11.x, t1.x, -m10.y * t0.y); r1.y = fma(m11.x, t1.y, m10.y * t0.x);
+    } else if (FORM == U1_SWAP) {
+        r0 = t1; r1 = t0;
+    } else {
+        r0 = cmul(m00, t0); cfma(r0, m01, t1);
+        r1 = cmul(m10, t0); cfma(r1, m11, t1);
     }
+    a0 = r0; a1 = r1;
 }
 
+// 2x2 gate on register bit J, no register-bit control
+template <typename R, int NX, int J, int FORM>
+__device__ __forceinline__ void u1_free(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M) {
+    using C = typename CxT<R>::T;
+    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+    for (int x0 = 0; x0 < NX; ++x0)
+        if (!(x0 & (1 << J))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
+}
+// ... controlled by register bit CB (must be 1)
+template <typename R, int NX, int J, int CB, int FORM>
+__device__ __forceinline__ void u1_ctrl(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M) {
+    using C = typename CxT<R>::T;
+    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+    for (int x0 = 0; x0 < NX; ++x0)
+        if (!(x0 & (1 << J)) && (x0 & (1 << CB))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
+}
+// ... any register-bit control pattern, checked per pair (uniform across the CTA)
 template <typename R, int NX, int J>
-__device__ __forceinline__ void u1_dispatch(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
-                                            int form, bool ctrl, uint32_t rc, uint32_t rv, bool tp) {
-    if (!ctrl) {
-        switch (form) {
-            case U1_REAL: u1_apply<R, NX, J, U1_REAL, false>(a, M, 0, 0, true); break;
-            case U1_RXLIKE: u1_apply<R, NX, J, U1_RXLIKE, false>(a, M, 0, 0, true); break;
-            case U1_ANTIDIAG: u1_apply<R, NX, J, U1_ANTIDIAG, false>(a, M, 0, 0, true); break;
-            case U1_SWAP: u1_apply<R, NX, J, U1_SWAP, false>(a, M, 0, 0, true); break;
-            default: u1_apply<R, NX, J, U1_GENERAL, false>(a, M, 0, 0, true); break;
+__device__ __forceinline__ void u1_masked(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
+                                          uint32_t rc, uint32_t rv) {
+    using C = typename CxT<R>::T;
+    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+    for (int x0 = 0; x0 < NX; ++x0)
+        if (!(x0 & (1 << J)) && ((uint32_t)x0 & rc) == rv)
+            butterfly<R, U1_GENERAL>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
+}
+// phase on the amplitudes whose register bits in MASK are all 1
+template <typename R, int NX, int MASK, int FORM>
+__device__ __forceinline__ void phase_bits(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T d) {
+#pragma unroll
+    for (int x = 0; x < NX; ++x)
+        if ((x & MASK) == MASK) {
+            if (FORM == PHASE_NEG) { a[x].x = -a[x].x; a[x].y = -a[x].y; }
+            else a[x] = cmul(d, a[x]);
         }
-    } else {
-        switch (form) {
-            case U1_REAL: u1_apply<R, NX, J, U1_REAL, true>(a, M, rc, rv, tp); break;
-            case U1_RXLIKE: u1_apply<R, NX, J, U1_RXLIKE, true>(a, M, rc, rv, tp); break;
-            case U1_ANTIDIAG: u1_apply<R, NX, J, U1_ANTIDIAG, true>(a, M, rc, rv, tp); break;
-            case U1_SWAP: u1_apply<R, NX, J, U1_SWAP, true>(a, M, rc, rv, tp); break;
-            default: u1_apply<R, NX, J, U1_GENERAL, true>(a, M, rc, rv, tp); break;
-        }
+}
+
+// class ids (RegOp::code): see plan_regop() on the host
+constexpr int CLS_U1F = 0;      // + j * 4 + form            (16)
+constexpr int CLS_U1C = 16;     // + (j * 4 + cb) * 2 + swap (32)
+constexpr int CLS_U1G = 48;     // + j                       (4)
+constexpr int CLS_PH1 = 52;     // + j * 2 + neg             (8)
+constexpr int CLS_PH2 = 60;     // + pair * 2 + neg          (12), pair over j1 < j2
+constexpr int CLS_PHT = 72;     // + neg : uniform over the thread's amplitudes
+constexpr int CLS_PHG = 74;     // any (care, value) pattern over the register bits
+
+template <typename R, int RB>
+__device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], typename CxT<R>::T &ph, int cls,
+                                          const typename CxT<R>::T *__restrict__ M, uint32_t rc, uint32_t rv) {
+    using C = typename CxT<R>::T;
+    constexpr int NX = 1 << RB;
+#define QCS_U1F(J, F) case CLS_U1F + (J) * 4 + (F): if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), F>(a, M); break;
+#define QCS_U1F_J(J) QCS_U1F(J, U1_GENERAL) QCS_U1F(J, U1_REAL) QCS_U1F(J, U1_RXLIKE) QCS_U1F(J, 3)
+#define QCS_U1C(J, CB) \
+    case CLS_U1C + ((J) * 4 + (CB)) * 2: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M); break; \
+    case CLS_U1C + ((J) * 4 + (CB)) * 2 + 1: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_SWAP>(a, M); break;
+#define QCS_PH1(J) \
+    case CLS_PH1 + (J) * 2: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, M[0]); break; \
+    case CLS_PH1 + (J) * 2 + 1: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_NEG>(a, M[0]); break;
+#define QCS_PH2(P, J1, J2) \
+    case CLS_PH2 + (P) * 2: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, M[0]); break; \
+    case CLS_PH2 + (P) * 2 + 1: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_NEG>(a, M[0]); break;
+    switch (cls) {
+        QCS_U1F_J(0) QCS_U1F_J(1) QCS_U1F_J(2) QCS_U1F_J(3)
+        QCS_U1C(0, 1) QCS_U1C(0, 2) QCS_U1C(0, 3) QCS_U1C(1, 0) QCS_U1C(1, 2) QCS_U1C(1, 3)
+        QCS_U1C(2, 0) QCS_U1C(2, 1) QCS_U1C(2, 3) QCS_U1C(3, 0) QCS_U1C(3, 1) QCS_U1C(3, 2)
+        case CLS_U1G + 0: u1_masked<R, NX, 0>(a, M, rc, rv); break;
+        case CLS_U1G + 1: if (1 < RB) u1_masked<R, NX, (1 < RB ? 1 : 0)>(a, M, rc, rv); break;
+        case CLS_U1G + 2: if (2 < RB) u1_masked<R, NX, (2 < RB ? 2 : 0)>(a, M, rc, rv); break;
+        case CLS_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv); break;
+        QCS_PH1(0) QCS_PH1(1) QCS_PH1(2) QCS_PH1(3)
+        QCS_PH2(0, 0, 1) QCS_PH2(1, 0, 2) QCS_PH2(2, 0, 3) QCS_PH2(3, 1, 2) QCS_PH2(4, 1, 3) QCS_PH2(5, 2, 3)
+        case CLS_PHT: ph = cmul(M[0], ph); break;
+        case CLS_PHT + 1: ph.x = -ph.x; ph.y = -ph.y; break;
+        default: {   // CLS_PHG
+            const C d = M[0];
+#pragma unroll
+            for (uint32_t x = 0; x < (uint32_t)NX; ++x)
+                if ((x & rc) == rv) a[x] = cmul(d, a[x]);
+        } break;
     }
+#undef QCS_U1F
+#undef QCS_U1F_J
+#undef QCS_U1C
+#undef QCS_PH1
+#undef QCS_PH2
 }
 
 // MT > 0: the tile has exactly MT bits, every sweep uses RB register bits (compile-time trip counts).
@@ -217,34 +275,10 @@ __device__ __forceinline__ void reg_sweep_impl(typename CxT<R>::T *tile, int m_r
         for (int o = 0; o < nops; ++o) {
             const uint4 w = ops4[o];                         // one broadcast 128-bit load per op
             const int slot = (int)w.w;
-            if (slot >= 0 && !((outer_ok >> slot) & 1ull)) continue;             // tile-uniform predicate
-            const uint32_t code = w.x & 0xffffu, rc = (w.x >> 16) & 0xffu, rv = w.x >> 24;
+            const bool tile_ok = slot < 0 || ((outer_ok >> slot) & 1ull);        // tile-uniform predicate
             const uint32_t bcare = w.y & 0xffffu, bval = w.y >> 16;
-            const bool tp = (base & bcare) == bval;                              // per-thread predicate
-            const C *M = pool + (int)w.z;
-            const int form = (int)(code >> 4);
-            if ((code & 3u) == REGOP_PHASE) {
-                const C d = M[0];
-                if (rc == 0) {
-                    if (tp) ph = form == PHASE_NEG ? cx<R>(-ph.x, -ph.y) : cmul(d, ph);
-                } else if (form == PHASE_NEG) {
-#pragma unroll
-                    for (uint32_t x = 0; x < NX; ++x)
-                        if (((x & rc) == rv) && tp) { a[x].x = -a[x].x; a[x].y = -a[x].y; }
-                } else {
-#pragma unroll
-                    for (uint32_t x = 0; x < NX; ++x)
-                        if (((x & rc) == rv) && tp) a[x] = cmul(d, a[x]);
-                }
-            } else {
-                const bool ctrl = (rc | bcare) != 0;
-                switch ((code >> 2) & 3u) {
-                    case 0: u1_dispatch<R, NX, 0>(a, M, form, ctrl, rc, rv, tp); break;
-                    case 1: u1_dispatch<R, NX, (RB > 1 ? 1 : 0)>(a, M, form, ctrl, rc, rv, tp); break;
-                    case 2: u1_dispatch<R, NX, (RB > 2 ? 2 : 0)>(a, M, form, ctrl, rc, rv, tp); break;
-                    default: u1_dispatch<R, NX, (RB > 3 ? 3 : 0)>(a, M, form, ctrl, rc, rv, tp); break;
-                }
-            }
+            if (tile_ok && (base & bcare) == bval)                               // per-thread predicate
+                run_regop<R, RB>(a, ph, (int)(w.x & 0xffffu), pool + (int)w.z, (w.x >> 16) & 0xffu, w.x >> 24);
         }
         if (sw.thread_phase) {
 #pragma unroll
@@ -734,6 +768,7 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
             else if (fast13) kern = tile_kernel_pipe<R, Prog, MSTD + 1, 2>;
         }
         S = S > TILE_MAX_STAGES ? TILE_MAX_STAGES : S;
+        while (S > 2 && (size_t)S * stage_bytes + prog > TILE_SMEM_BUDGET) --S;
         const int tuned = tune_int("QCS_PIPE_STAGES", S);
         if (tuned < S) S = tuned;
         if (S < 2) S = 2;
@@ -957,12 +992,20 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 const double *M = o.matrix;   // m00 m01 m10 m11 as (re, im)
                 const bool real = M[1] == 0 && M[3] == 0 && M[5] == 0 && M[7] == 0;
                 const bool rxl = M[1] == 0 && M[7] == 0 && M[2] == 0 && M[4] == 0;
-                const bool anti = M[0] == 0 && M[1] == 0 && M[6] == 0 && M[7] == 0;
-                const bool swp = anti && M[2] == 1 && M[3] == 0 && M[4] == 1 && M[5] == 0;
-                const int form = swp ? U1_SWAP : real ? U1_REAL : anti ? U1_ANTIDIAG : rxl ? U1_RXLIKE : U1_GENERAL;
-                r.code = (uint16_t)(REGOP_U1 | (j << 2) | (form << 4));
+                const bool swp = M[0] == 0 && M[1] == 0 && M[6] == 0 && M[7] == 0 && M[2] == 1 && M[3] == 0 &&
+                                 M[4] == 1 && M[5] == 0;
                 if (!split_masks(o.ctrl_mask, o.ctrl_mask, r))
                     return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
+                const int nrc = __builtin_popcount(r.reg_care);
+                if (nrc == 0) {
+                    const int form = swp ? 3 : real ? U1_REAL : rxl ? U1_RXLIKE : U1_GENERAL;
+                    r.code = (uint16_t)(CLS_U1F + j * 4 + form);
+                } else if (nrc == 1) {
+                    const int cb = __builtin_ctz(r.reg_care);
+                    r.code = (uint16_t)(CLS_U1C + (j * 4 + cb) * 2 + (swp ? 1 : 0));
+                } else {
+                    r.code = (uint16_t)(CLS_U1G + j);
+                }
                 const int at = push_entries(M, 4);
                 if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
                 r.mat = at;
@@ -988,8 +1031,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     if (re == 1.0 && im == 0.0) continue;
                     if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
                     RegOp &r = P.regops[P.nregops++];
-                    const int form = (re == -1.0 && im == 0.0) ? PHASE_NEG : PHASE_GENERAL;
-                    r.code = (uint16_t)(REGOP_PHASE | (form << 4));
+                    const int neg = (re == -1.0 && im == 0.0) ? 1 : 0;
                     uint64_t care = o.ctrl_mask, val = o.ctrl_mask;
                     for (int j = 0; j < o.k; ++j) {
                         care |= 1ull << o.bitpos[j];
@@ -997,7 +1039,19 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     }
                     if (!split_masks(care, val, r))
                         return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
-                    if (r.reg_care == 0) sw.thread_phase = 1;
+                    const int nrc = __builtin_popcount(r.reg_care);
+                    if (nrc == 0) {
+                        r.code = (uint16_t)(CLS_PHT + neg);
+                        sw.thread_phase = 1;
+                    } else if (nrc == 1 && r.reg_val == r.reg_care) {
+                        r.code = (uint16_t)(CLS_PH1 + __builtin_ctz(r.reg_care) * 2 + neg);
+                    } else if (nrc == 2 && r.reg_val == r.reg_care) {
+                        const int j1 = __builtin_ctz(r.reg_care), j2 = 31 - __builtin_clz((unsigned)r.reg_care);
+                        static const int pair_index[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+                        r.code = (uint16_t)(CLS_PH2 + pair_index[j1][j2] * 2 + neg);
+                    } else {
+                        r.code = (uint16_t)CLS_PHG;
+                    }
                     const double d[2] = {re, im};
                     const int at = push_entries(d, 1);
                     if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
