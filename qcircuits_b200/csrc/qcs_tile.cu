@@ -130,19 +130,37 @@ __device__ __forceinline__ void butterfly(typename CxT<R>::T &a0, typename CxT<R
 }
 
 // 2x2 gate on register bit J, no register-bit control
+// Coefficients of an op for this thread: the op's own when its per-thread / per-tile predicate holds, the
+// identity otherwise.  Substituting coefficients instead of branching keeps the op loop free of divergent
+// regions (the register allocator otherwise copies all 2^RB amplitudes into and out of every region).
+template <typename C>
+__device__ __forceinline__ void load_matrix(const C *__restrict__ M, bool ok, C &m00, C &m01, C &m10, C &m11) {
+    m00 = M[0]; m01 = M[1]; m10 = M[2]; m11 = M[3];
+    if (!ok) {
+        m00.x = 1; m00.y = 0; m01.x = 0; m01.y = 0; m10.x = 0; m10.y = 0; m11.x = 1; m11.y = 0;
+    }
+}
+template <typename C> __device__ __forceinline__ C load_phase(const C *__restrict__ M, bool ok) {
+    C d = M[0];
+    if (!ok) { d.x = 1; d.y = 0; }
+    return d;
+}
+
 template <typename R, int NX, int J, int FORM>
-__device__ __forceinline__ void u1_free(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M) {
+__device__ __forceinline__ void u1_free(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M, bool ok) {
     using C = typename CxT<R>::T;
-    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+    C m00, m01, m10, m11;
+    load_matrix(M, ok, m00, m01, m10, m11);
 #pragma unroll
     for (int x0 = 0; x0 < NX; ++x0)
         if (!(x0 & (1 << J))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
 }
 // ... controlled by register bit CB (must be 1)
 template <typename R, int NX, int J, int CB, int FORM>
-__device__ __forceinline__ void u1_ctrl(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M) {
+__device__ __forceinline__ void u1_ctrl(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M, bool ok) {
     using C = typename CxT<R>::T;
-    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+    C m00, m01, m10, m11;
+    load_matrix(M, ok, m00, m01, m10, m11);
 #pragma unroll
     for (int x0 = 0; x0 < NX; ++x0)
         if (!(x0 & (1 << J)) && (x0 & (1 << CB))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
@@ -150,9 +168,10 @@ __device__ __forceinline__ void u1_ctrl(typename CxT<R>::T (&a)[NX], const typen
 // ... any register-bit control pattern, checked per pair (uniform across the CTA)
 template <typename R, int NX, int J>
 __device__ __forceinline__ void u1_masked(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
-                                          uint32_t rc, uint32_t rv) {
+                                          uint32_t rc, uint32_t rv, bool ok) {
     using C = typename CxT<R>::T;
-    const C m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+    C m00, m01, m10, m11;
+    load_matrix(M, ok, m00, m01, m10, m11);
 #pragma unroll
     for (int x0 = 0; x0 < NX; ++x0)
         if (!(x0 & (1 << J)) && ((uint32_t)x0 & rc) == rv)
@@ -180,34 +199,34 @@ constexpr int CLS_PHG = 74;     // any (care, value) pattern over the register b
 
 template <typename R, int RB>
 __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], typename CxT<R>::T &ph, int cls,
-                                          const typename CxT<R>::T *__restrict__ M, uint32_t rc, uint32_t rv) {
+                                          const typename CxT<R>::T *__restrict__ M, uint32_t rc, uint32_t rv, bool ok) {
     using C = typename CxT<R>::T;
     constexpr int NX = 1 << RB;
-#define QCS_U1F(J, F) case CLS_U1F + (J) * 4 + (F): if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), F>(a, M); break;
+#define QCS_U1F(J, F) case CLS_U1F + (J) * 4 + (F): if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), F>(a, M, ok); break;
 #define QCS_U1F_J(J) QCS_U1F(J, U1_GENERAL) QCS_U1F(J, U1_REAL) QCS_U1F(J, U1_RXLIKE) QCS_U1F(J, 3)
 #define QCS_U1C(J, CB) \
-    case CLS_U1C + ((J) * 4 + (CB)) * 2: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M); break; \
-    case CLS_U1C + ((J) * 4 + (CB)) * 2 + 1: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_SWAP>(a, M); break;
+    case CLS_U1C + ((J) * 4 + (CB)) * 2: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M, ok); break; \
+    case CLS_U1C + ((J) * 4 + (CB)) * 2 + 1: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_SWAP>(a, M, ok); break;
 #define QCS_PH1(J) \
-    case CLS_PH1 + (J) * 2: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, M[0]); break; \
+    case CLS_PH1 + (J) * 2: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, load_phase(M, ok)); break; \
     case CLS_PH1 + (J) * 2 + 1: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_NEG>(a, M[0]); break;
 #define QCS_PH2(P, J1, J2) \
-    case CLS_PH2 + (P) * 2: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, M[0]); break; \
+    case CLS_PH2 + (P) * 2: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, load_phase(M, ok)); break; \
     case CLS_PH2 + (P) * 2 + 1: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_NEG>(a, M[0]); break;
     switch (cls) {
         QCS_U1F_J(0) QCS_U1F_J(1) QCS_U1F_J(2) QCS_U1F_J(3)
         QCS_U1C(0, 1) QCS_U1C(0, 2) QCS_U1C(0, 3) QCS_U1C(1, 0) QCS_U1C(1, 2) QCS_U1C(1, 3)
         QCS_U1C(2, 0) QCS_U1C(2, 1) QCS_U1C(2, 3) QCS_U1C(3, 0) QCS_U1C(3, 1) QCS_U1C(3, 2)
-        case CLS_U1G + 0: u1_masked<R, NX, 0>(a, M, rc, rv); break;
-        case CLS_U1G + 1: if (1 < RB) u1_masked<R, NX, (1 < RB ? 1 : 0)>(a, M, rc, rv); break;
-        case CLS_U1G + 2: if (2 < RB) u1_masked<R, NX, (2 < RB ? 2 : 0)>(a, M, rc, rv); break;
-        case CLS_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv); break;
+        case CLS_U1G + 0: u1_masked<R, NX, 0>(a, M, rc, rv, ok); break;
+        case CLS_U1G + 1: if (1 < RB) u1_masked<R, NX, (1 < RB ? 1 : 0)>(a, M, rc, rv, ok); break;
+        case CLS_U1G + 2: if (2 < RB) u1_masked<R, NX, (2 < RB ? 2 : 0)>(a, M, rc, rv, ok); break;
+        case CLS_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv, ok); break;
         QCS_PH1(0) QCS_PH1(1) QCS_PH1(2) QCS_PH1(3)
         QCS_PH2(0, 0, 1) QCS_PH2(1, 0, 2) QCS_PH2(2, 0, 3) QCS_PH2(3, 1, 2) QCS_PH2(4, 1, 3) QCS_PH2(5, 2, 3)
-        case CLS_PHT: ph = cmul(M[0], ph); break;
+        case CLS_PHT: ph = cmul(load_phase(M, ok), ph); break;
         case CLS_PHT + 1: ph.x = -ph.x; ph.y = -ph.y; break;
         default: {   // CLS_PHG
-            const C d = M[0];
+            const C d = load_phase(M, ok);
 #pragma unroll
             for (uint32_t x = 0; x < (uint32_t)NX; ++x)
                 if ((x & rc) == rv) a[x] = cmul(d, a[x]);
@@ -221,13 +240,14 @@ __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], type
 }
 
 // MT > 0: the tile has exactly MT bits, every sweep uses RB register bits (compile-time trip counts).
-// VEC   : complex64 with tile bit 0 among the register bits -> amplitude pairs move as one 128-bit access.
-template <typename R, int RB, typename Layout, int MT, bool VEC>
-__device__ __forceinline__ void reg_sweep_impl(typename CxT<R>::T *tile, int m_rt, const Sweep &sw, const RegOp *rops,
-                                               const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
+template <typename R, int RB, typename Layout, int MT>
+__device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, const Sweep &sw, const RegOp *rops,
+                                          const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
     using C = typename CxT<R>::T;
     constexpr int NX = 1 << RB;
     constexpr bool FAST = MT > 0;
+    // complex64 with tile bit 0 among the register bits: amplitude pairs move as one 128-bit access
+    const bool VEC = sizeof(C) == 8 && sw.nreg >= 1 && sw.rpos[0] == 0;
     const int m = FAST ? MT : m_rt;
     const int nreg = FAST ? RB : sw.nreg;
     const uint32_t nx_used = 1u << nreg;
@@ -277,8 +297,8 @@ __device__ __forceinline__ void reg_sweep_impl(typename CxT<R>::T *tile, int m_r
             const int slot = (int)w.w;
             const bool tile_ok = slot < 0 || ((outer_ok >> slot) & 1ull);        // tile-uniform predicate
             const uint32_t bcare = w.y & 0xffffu, bval = w.y >> 16;
-            if (tile_ok && (base & bcare) == bval)                               // per-thread predicate
-                run_regop<R, RB>(a, ph, (int)(w.x & 0xffffu), pool + (int)w.z, (w.x >> 16) & 0xffu, w.x >> 24);
+            const bool ok = tile_ok && (base & bcare) == bval;                   // per-thread predicate
+            run_regop<R, RB>(a, ph, (int)(w.x & 0xffffu), pool + (int)w.z, (w.x >> 16) & 0xffu, w.x >> 24, ok);
         }
         if (sw.thread_phase) {
 #pragma unroll
@@ -299,16 +319,6 @@ __device__ __forceinline__ void reg_sweep_impl(typename CxT<R>::T *tile, int m_r
                 if (FAST || x < nx_used) tile[addr[x]] = a[x];
         }
     }
-}
-
-template <typename R, int RB, typename Layout, int MT>
-__device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m, const Sweep &sw, const RegOp *rops,
-                                          const typename CxT<R>::T *pool, uint64_t outer_ok, int tid, int nt) {
-    using C = typename CxT<R>::T;
-    if (sizeof(C) == 8 && sw.nreg >= 1 && sw.rpos[0] == 0)
-        reg_sweep_impl<R, RB, Layout, MT, sizeof(C) == 8>(tile, m, sw, rops, pool, outer_ok, tid, nt);
-    else
-        reg_sweep_impl<R, RB, Layout, MT, false>(tile, m, sw, rops, pool, outer_ok, tid, nt);
 }
 
 // The program as staged in shared memory.
@@ -997,12 +1007,14 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 if (!split_masks(o.ctrl_mask, o.ctrl_mask, r))
                     return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
                 const int nrc = __builtin_popcount(r.reg_care);
+                const bool conditional = r.base_care != 0 || r.outer_slot >= 0;   // predicate = coefficient substitution
+                const bool swp_ok = swp && !conditional;
                 if (nrc == 0) {
-                    const int form = swp ? 3 : real ? U1_REAL : rxl ? U1_RXLIKE : U1_GENERAL;
+                    const int form = swp_ok ? 3 : real ? U1_REAL : rxl ? U1_RXLIKE : U1_GENERAL;
                     r.code = (uint16_t)(CLS_U1F + j * 4 + form);
                 } else if (nrc == 1) {
                     const int cb = __builtin_ctz(r.reg_care);
-                    r.code = (uint16_t)(CLS_U1C + (j * 4 + cb) * 2 + (swp ? 1 : 0));
+                    r.code = (uint16_t)(CLS_U1C + (j * 4 + cb) * 2 + (swp_ok ? 1 : 0));
                 } else {
                     r.code = (uint16_t)(CLS_U1G + j);
                 }
@@ -1031,7 +1043,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     if (re == 1.0 && im == 0.0) continue;
                     if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
                     RegOp &r = P.regops[P.nregops++];
-                    const int neg = (re == -1.0 && im == 0.0) ? 1 : 0;
+                    const bool neg0 = (re == -1.0 && im == 0.0);
                     uint64_t care = o.ctrl_mask, val = o.ctrl_mask;
                     for (int j = 0; j < o.k; ++j) {
                         care |= 1ull << o.bitpos[j];
@@ -1040,6 +1052,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     if (!split_masks(care, val, r))
                         return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
                     const int nrc = __builtin_popcount(r.reg_care);
+                    const int neg = (neg0 && r.base_care == 0 && r.outer_slot < 0) ? 1 : 0;
                     if (nrc == 0) {
                         r.code = (uint16_t)(CLS_PHT + neg);
                         sw.thread_phase = 1;
