@@ -45,14 +45,14 @@ def tile_limits(dtype):
     return low.value, tile.value
 
 
-def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512):
+def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None):
     """Greedy fusion: repeatedly pick the tile (low bits + a window of high bits) that admits the most
     pending gates, where a gate may overtake an earlier one only if they commute (they share no bit on
     which either acts non-diagonally).  ``gates`` are records with nd_mask / d_mask / entries / wide over
     the n flat bits of the (local) state.  Returns lists of indices into ``gates``."""
     low, tile = tile_limits(dtype)
     L = min(low, n)
-    hcap = max(0, min(tile - low, n - L))
+    hcap = max(0, min(tile - low if high_bits is None else high_bits, n - L))
     low_mask = (1 << L) - 1
     pool_cap = 12288 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
     max_ops = min(max_ops, _lib.QCS_MAX_OPS)

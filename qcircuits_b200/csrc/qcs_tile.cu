@@ -489,16 +489,24 @@ __device__ __forceinline__ void vec_norm_acc(double &acc, const uint4 v, double)
 // MT > 0: compile-time geometry -- the tile has MT bits, its low LSTD bits are contiguous, the CTA has
 // TILE_THREADS threads; every staging loop has a constant trip count.  MT == 0: everything at run time
 // (small states, unusual tiles).
+// threads per CTA of an instantiation: the 64 KB tiles (one CTA per SM) get 512 threads so that the SM
+// still holds 16 warps
+template <typename R, int MT> struct PipeThreads {
+    static constexpr int MSTD = sizeof(typename CxT<R>::T) == 8 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
+    static constexpr int value = MT == MSTD + 1 ? 2 * TILE_THREADS : TILE_THREADS;
+};
+
 template <typename R, typename Prog, int MT, int OCC>
-__global__ void __launch_bounds__(TILE_THREADS, OCC) tile_kernel_pipe(const __grid_constant__ Prog P) {
+__global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_pipe(const __grid_constant__ Prog P) {
     using C = typename CxT<R>::T;
     using Layout = PaddedLayout<C>;
     constexpr bool FAST = MT > 0;
+    constexpr int NT = PipeThreads<R, MT>::value;
     constexpr int LSTD = sizeof(C) == 8 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
     constexpr int VSHIFT = sizeof(C) == 8 ? 1 : 0;       // amplitudes per 16-byte vector = 1 << VSHIFT
     extern __shared__ __align__(128) unsigned char smem_all[];
     const int tid = threadIdx.x;
-    const int nt = FAST ? TILE_THREADS : (int)blockDim.x;
+    const int nt = FAST ? NT : (int)blockDim.x;
     ProgView pv;
     const uint64_t *chunk_off;
     const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, nt);
@@ -751,21 +759,19 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         const bool fast_ok = P.L == LSTD && tune_int("QCS_PIPE_GENERIC", 0) == 0;
         int ctas = tune_int("QCS_PIPE_CTAS", 2);
         if (ctas < 1) ctas = 1;
-        if (ctas > 3) ctas = 3;
+        if (ctas > 2) ctas = 2;
         const bool fast12 = fast_ok && m == MSTD, fast13 = fast_ok && m == MSTD + 1;
         if (!(fast12 || fast13) && ctas > 2) ctas = 2;
         void (*kern)(const Prog) = tile_kernel_pipe<R, Prog, 0, 2>;
-        if (fast12) kern = ctas == 3 ? tile_kernel_pipe<R, Prog, MSTD, 3> : tile_kernel_pipe<R, Prog, MSTD, 2>;
-        else if (fast13) kern = ctas == 3 ? tile_kernel_pipe<R, Prog, MSTD + 1, 3> : tile_kernel_pipe<R, Prog, MSTD + 1, 2>;
+        if (fast12) kern = tile_kernel_pipe<R, Prog, MSTD, 2>;
+        else if (fast13) { kern = tile_kernel_pipe<R, Prog, MSTD + 1, 1>; ctas = 1; }
         const bool is_fast = fast12 || fast13;
         static bool attr_done = false;
         if (!attr_done) {
             const int lim = (int)TILE_SMEM_BUDGET;
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             attr_done = true;
         }
         const size_t stage_bytes = PaddedLayout<C>::bytes(m);
@@ -775,7 +781,6 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
             --ctas;
             S = (int)((sm_smem / ctas - prog - 1024) / stage_bytes);
             if (fast12) kern = tile_kernel_pipe<R, Prog, MSTD, 2>;
-            else if (fast13) kern = tile_kernel_pipe<R, Prog, MSTD + 1, 2>;
         }
         S = S > TILE_MAX_STAGES ? TILE_MAX_STAGES : S;
         while (S > 2 && (size_t)S * stage_bytes + prog > TILE_SMEM_BUDGET) --S;
@@ -788,7 +793,7 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         uint64_t grid = (uint64_t)dev.sms * ctas;
         if (grid > P.ntiles) grid = P.ntiles;
         if (grid > MAX_GRID) grid = MAX_GRID;
-        int threads = TILE_THREADS;
+        int threads = fast13 ? 2 * TILE_THREADS : TILE_THREADS;
         if (!is_fast)
             while (threads > 32 && (1u << m) < (unsigned)threads * 2u) threads >>= 1;
         kern<<<(unsigned)grid, threads, smem, stream>>>(P);
