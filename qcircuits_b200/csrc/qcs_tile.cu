@@ -202,17 +202,21 @@ __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], type
                                           const typename CxT<R>::T *__restrict__ M, uint32_t rc, uint32_t rv, bool ok) {
     using C = typename CxT<R>::T;
     constexpr int NX = 1 << RB;
-#define QCS_U1F(J, F) case CLS_U1F + (J) * 4 + (F): if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), F>(a, M, ok); break;
-#define QCS_U1F_J(J) QCS_U1F(J, U1_GENERAL) QCS_U1F(J, U1_REAL) QCS_U1F(J, U1_RXLIKE) QCS_U1F(J, 3)
+    // All arithmetic forms share one body per register position: with ~30 arms ptxas keeps the 2^RB
+    // amplitudes in place across the switch; with one arm per (position, form) it copied all of them into
+    // and out of every arm (ncu: MOV = 27 % of the instructions of a fused pass, ALU pipe 62 % busy).
+#define QCS_U1F_J(J) \
+    case CLS_U1F + (J) * 4: case CLS_U1F + (J) * 4 + 1: case CLS_U1F + (J) * 4 + 2: case CLS_U1F + (J) * 4 + 3: \
+        if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), U1_GENERAL>(a, M, ok); break;
 #define QCS_U1C(J, CB) \
-    case CLS_U1C + ((J) * 4 + (CB)) * 2: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M, ok); break; \
-    case CLS_U1C + ((J) * 4 + (CB)) * 2 + 1: if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_SWAP>(a, M, ok); break;
+    case CLS_U1C + ((J) * 4 + (CB)) * 2: case CLS_U1C + ((J) * 4 + (CB)) * 2 + 1: \
+        if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M, ok); break;
 #define QCS_PH1(J) \
-    case CLS_PH1 + (J) * 2: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, load_phase(M, ok)); break; \
-    case CLS_PH1 + (J) * 2 + 1: if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_NEG>(a, M[0]); break;
+    case CLS_PH1 + (J) * 2: case CLS_PH1 + (J) * 2 + 1: \
+        if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, load_phase(M, ok)); break;
 #define QCS_PH2(P, J1, J2) \
-    case CLS_PH2 + (P) * 2: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, load_phase(M, ok)); break; \
-    case CLS_PH2 + (P) * 2 + 1: if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_NEG>(a, M[0]); break;
+    case CLS_PH2 + (P) * 2: case CLS_PH2 + (P) * 2 + 1: \
+        if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, load_phase(M, ok)); break;
     switch (cls) {
         QCS_U1F_J(0) QCS_U1F_J(1) QCS_U1F_J(2) QCS_U1F_J(3)
         QCS_U1C(0, 1) QCS_U1C(0, 2) QCS_U1C(0, 3) QCS_U1C(1, 0) QCS_U1C(1, 2) QCS_U1C(1, 3)
@@ -223,8 +227,7 @@ __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], type
         case CLS_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv, ok); break;
         QCS_PH1(0) QCS_PH1(1) QCS_PH1(2) QCS_PH1(3)
         QCS_PH2(0, 0, 1) QCS_PH2(1, 0, 2) QCS_PH2(2, 0, 3) QCS_PH2(3, 1, 2) QCS_PH2(4, 1, 3) QCS_PH2(5, 2, 3)
-        case CLS_PHT: ph = cmul(load_phase(M, ok), ph); break;
-        case CLS_PHT + 1: ph.x = -ph.x; ph.y = -ph.y; break;
+        case CLS_PHT: case CLS_PHT + 1: ph = cmul(load_phase(M, ok), ph); break;
         default: {   // CLS_PHG
             const C d = load_phase(M, ok);
 #pragma unroll
@@ -232,7 +235,6 @@ __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], type
                 if ((x & rc) == rv) a[x] = cmul(d, a[x]);
         } break;
     }
-#undef QCS_U1F
 #undef QCS_U1F_J
 #undef QCS_U1C
 #undef QCS_PH1
