@@ -188,14 +188,15 @@ __device__ __forceinline__ void phase_bits(typename CxT<R>::T (&a)[NX], const ty
         }
 }
 
-// class ids (RegOp::code): see plan_regop() on the host
-constexpr int CLS_U1F = 0;      // + j * 4 + form            (16)
-constexpr int CLS_U1C = 16;     // + (j * 4 + cb) * 2 + swap (32)
-constexpr int CLS_U1G = 48;     // + j                       (4)
-constexpr int CLS_PH1 = 52;     // + j * 2 + neg             (8)
-constexpr int CLS_PH2 = 60;     // + pair * 2 + neg          (12), pair over j1 < j2
-constexpr int CLS_PHT = 72;     // + neg : uniform over the thread's amplitudes
-constexpr int CLS_PHG = 74;     // any (care, value) pattern over the register bits
+// arm ids (RegOp::code), dense so that the dispatch is one jump table
+constexpr int ARM_U1F = 0;      // + j                              (4)  2x2 on register bit j
+constexpr int ARM_U1C = 4;      // + j * 3 + rank of cb among != j   (12) ... controlled by register bit cb
+constexpr int ARM_U1G = 16;     // + j                              (4)  ... any register-bit control pattern
+constexpr int ARM_PH1 = 20;     // + j                              (4)  phase where register bit j is 1
+constexpr int ARM_PH2 = 24;     // + pair(j1 < j2)                  (6)  phase where both bits are 1
+constexpr int ARM_PHT = 30;     // phase uniform over the thread's amplitudes
+constexpr int ARM_PHG = 31;     // phase on any (care, value) pattern over the register bits
+__host__ __device__ constexpr int u1c_arm(int j, int cb) { return ARM_U1C + j * 3 + (cb < j ? cb : cb - 1); }
 
 template <typename R, int RB>
 __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], typename CxT<R>::T &ph, int cls,
@@ -205,30 +206,25 @@ __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], type
     // All arithmetic forms share one body per register position: with ~30 arms ptxas keeps the 2^RB
     // amplitudes in place across the switch; with one arm per (position, form) it copied all of them into
     // and out of every arm (ncu: MOV = 27 % of the instructions of a fused pass, ALU pipe 62 % busy).
-#define QCS_U1F_J(J) \
-    case CLS_U1F + (J) * 4: case CLS_U1F + (J) * 4 + 1: case CLS_U1F + (J) * 4 + 2: case CLS_U1F + (J) * 4 + 3: \
-        if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), U1_GENERAL>(a, M, ok); break;
+#define QCS_U1F_J(J) case ARM_U1F + (J): if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), U1_GENERAL>(a, M, ok); break;
 #define QCS_U1C(J, CB) \
-    case CLS_U1C + ((J) * 4 + (CB)) * 2: case CLS_U1C + ((J) * 4 + (CB)) * 2 + 1: \
-        if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M, ok); break;
+    case u1c_arm(J, CB): if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M, ok); break;
 #define QCS_PH1(J) \
-    case CLS_PH1 + (J) * 2: case CLS_PH1 + (J) * 2 + 1: \
-        if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, load_phase(M, ok)); break;
+    case ARM_PH1 + (J): if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, load_phase(M, ok)); break;
 #define QCS_PH2(P, J1, J2) \
-    case CLS_PH2 + (P) * 2: case CLS_PH2 + (P) * 2 + 1: \
-        if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, load_phase(M, ok)); break;
+    case ARM_PH2 + (P): if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, load_phase(M, ok)); break;
     switch (cls) {
         QCS_U1F_J(0) QCS_U1F_J(1) QCS_U1F_J(2) QCS_U1F_J(3)
         QCS_U1C(0, 1) QCS_U1C(0, 2) QCS_U1C(0, 3) QCS_U1C(1, 0) QCS_U1C(1, 2) QCS_U1C(1, 3)
         QCS_U1C(2, 0) QCS_U1C(2, 1) QCS_U1C(2, 3) QCS_U1C(3, 0) QCS_U1C(3, 1) QCS_U1C(3, 2)
-        case CLS_U1G + 0: u1_masked<R, NX, 0>(a, M, rc, rv, ok); break;
-        case CLS_U1G + 1: if (1 < RB) u1_masked<R, NX, (1 < RB ? 1 : 0)>(a, M, rc, rv, ok); break;
-        case CLS_U1G + 2: if (2 < RB) u1_masked<R, NX, (2 < RB ? 2 : 0)>(a, M, rc, rv, ok); break;
-        case CLS_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv, ok); break;
+        case ARM_U1G + 0: u1_masked<R, NX, 0>(a, M, rc, rv, ok); break;
+        case ARM_U1G + 1: if (1 < RB) u1_masked<R, NX, (1 < RB ? 1 : 0)>(a, M, rc, rv, ok); break;
+        case ARM_U1G + 2: if (2 < RB) u1_masked<R, NX, (2 < RB ? 2 : 0)>(a, M, rc, rv, ok); break;
+        case ARM_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv, ok); break;
         QCS_PH1(0) QCS_PH1(1) QCS_PH1(2) QCS_PH1(3)
         QCS_PH2(0, 0, 1) QCS_PH2(1, 0, 2) QCS_PH2(2, 0, 3) QCS_PH2(3, 1, 2) QCS_PH2(4, 1, 3) QCS_PH2(5, 2, 3)
-        case CLS_PHT: case CLS_PHT + 1: ph = cmul(load_phase(M, ok), ph); break;
-        default: {   // CLS_PHG
+        case ARM_PHT: ph = cmul(load_phase(M, ok), ph); break;
+        default: {   // ARM_PHG
             const C d = load_phase(M, ok);
 #pragma unroll
             for (uint32_t x = 0; x < (uint32_t)NX; ++x)
@@ -1007,24 +1003,12 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 RegOp &r = P.regops[P.nregops++];
                 const int j = reg_index_of_local[local_of(o.bitpos[0])];
                 const double *M = o.matrix;   // m00 m01 m10 m11 as (re, im)
-                const bool real = M[1] == 0 && M[3] == 0 && M[5] == 0 && M[7] == 0;
-                const bool rxl = M[1] == 0 && M[7] == 0 && M[2] == 0 && M[4] == 0;
-                const bool swp = M[0] == 0 && M[1] == 0 && M[6] == 0 && M[7] == 0 && M[2] == 1 && M[3] == 0 &&
-                                 M[4] == 1 && M[5] == 0;
                 if (!split_masks(o.ctrl_mask, o.ctrl_mask, r))
                     return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
                 const int nrc = __builtin_popcount(r.reg_care);
-                const bool conditional = r.base_care != 0 || r.outer_slot >= 0;   // predicate = coefficient substitution
-                const bool swp_ok = swp && !conditional;
-                if (nrc == 0) {
-                    const int form = swp_ok ? 3 : real ? U1_REAL : rxl ? U1_RXLIKE : U1_GENERAL;
-                    r.code = (uint16_t)(CLS_U1F + j * 4 + form);
-                } else if (nrc == 1) {
-                    const int cb = __builtin_ctz(r.reg_care);
-                    r.code = (uint16_t)(CLS_U1C + (j * 4 + cb) * 2 + (swp_ok ? 1 : 0));
-                } else {
-                    r.code = (uint16_t)(CLS_U1G + j);
-                }
+                if (nrc == 0) r.code = (uint16_t)(ARM_U1F + j);
+                else if (nrc == 1) r.code = (uint16_t)u1c_arm(j, __builtin_ctz(r.reg_care));
+                else r.code = (uint16_t)(ARM_U1G + j);
                 const int at = push_entries(M, 4);
                 if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
                 r.mat = at;
@@ -1050,7 +1034,6 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     if (re == 1.0 && im == 0.0) continue;
                     if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
                     RegOp &r = P.regops[P.nregops++];
-                    const bool neg0 = (re == -1.0 && im == 0.0);
                     uint64_t care = o.ctrl_mask, val = o.ctrl_mask;
                     for (int j = 0; j < o.k; ++j) {
                         care |= 1ull << o.bitpos[j];
@@ -1059,18 +1042,17 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     if (!split_masks(care, val, r))
                         return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
                     const int nrc = __builtin_popcount(r.reg_care);
-                    const int neg = (neg0 && r.base_care == 0 && r.outer_slot < 0) ? 1 : 0;
                     if (nrc == 0) {
-                        r.code = (uint16_t)(CLS_PHT + neg);
+                        r.code = (uint16_t)ARM_PHT;
                         sw.thread_phase = 1;
                     } else if (nrc == 1 && r.reg_val == r.reg_care) {
-                        r.code = (uint16_t)(CLS_PH1 + __builtin_ctz(r.reg_care) * 2 + neg);
+                        r.code = (uint16_t)(ARM_PH1 + __builtin_ctz(r.reg_care));
                     } else if (nrc == 2 && r.reg_val == r.reg_care) {
                         const int j1 = __builtin_ctz(r.reg_care), j2 = 31 - __builtin_clz((unsigned)r.reg_care);
                         static const int pair_index[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
-                        r.code = (uint16_t)(CLS_PH2 + pair_index[j1][j2] * 2 + neg);
+                        r.code = (uint16_t)(ARM_PH2 + pair_index[j1][j2]);
                     } else {
-                        r.code = (uint16_t)CLS_PHG;
+                        r.code = (uint16_t)ARM_PHG;
                     }
                     const double d[2] = {re, im};
                     const int at = push_entries(d, 1);
