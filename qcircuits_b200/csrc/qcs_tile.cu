@@ -107,53 +107,38 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 // phase bits) is a template parameter, so a body is straight-line arithmetic on named registers with no
 // per-amplitude predicate; the class id of an op (RegOp::code) picks the body through one jump table.
 // Controls that are not register bits are one per-thread predicate around the whole body.
+template <typename R, int FORM>
+__device__ __forceinline__ void butterfly(typename CxT<R>::T &a0, typename CxT<R>::T &a1, const typename CxT<R>::T m00,
+                                          const typename CxT<R>::T m01, const typename CxT<R>::T m10,
+                                          const typename CxT<R>::T m11) {
+    using C = typename CxT<R>::T;
+    const C t0 = a0, t1 = a1;
+    C r0, r1;
+    if (FORM == U1_REAL) {
+        r0.x = fma(m00.x, t0.x, m01.x * t1.x); r0.y = fma(m00.x, t0.y, m01.x * t1.y);
+        r1.x = fma(m10.x, t0.x, m11.x * t1.x); r1.y = fma(m10.x, t0.y, m11.x * t1.y);
+    } else if (FORM == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
+        r0.x = fma(m00.x, t0.x, -m01.y * t1.y); r0.y = fma(m00.x, t0.y, m01.y * t1.x);
+        r1.x = fma(m11.x, t1.x, -m10.y * t0.y); r1.y = fma(m11.x, t1.y, m10.y * t0.x);
+    } else if (FORM == U1_SWAP) {
+        r0 = t1; r1 = t0;
+    } else {
+        r0 = cmul(m00, t0); cfma(r0, m01, t1);
+        r1 = cmul(m10, t0); cfma(r1, m11, t1);
+    }
+    a0 = r0; a1 = r1;
+}
+
+// 2x2 gate on register bit J, no register-bit control
 // Coefficients of an op for this thread: the op's own when its per-thread / per-tile predicate holds, the
 // identity otherwise.  Substituting coefficients instead of branching keeps the op loop free of divergent
 // regions (the register allocator otherwise copies all 2^RB amplitudes into and out of every region).
-//
-// complex64 uses Blackwell's packed FP32 pipe (FFMA2 / FMUL2: `fma.rn.f32x2`): with m = (mr, mi) and an
-// amplitude t = (tr, ti) held as one 64-bit register pair,  m t = (mr, mr) * t + (-mi, mi) * swap(t),
-// i.e. one packed multiply/FMA per term instead of two scalar ones (three-register FFMA issues every other
-// cycle per scheduler; the packed form doubles the FMA rate).  complex128 stays scalar FP64.
-template <typename R> struct Coef;
-template <> struct Coef<double> {
-    double2 m00, m01, m10, m11;
-    __device__ __forceinline__ void load(const double2 *__restrict__ M, bool ok) {
-        m00 = M[0]; m01 = M[1]; m10 = M[2]; m11 = M[3];
-        if (!ok) { m00 = make_double2(1, 0); m01 = make_double2(0, 0); m10 = make_double2(0, 0); m11 = make_double2(1, 0); }
+template <typename C>
+__device__ __forceinline__ void load_matrix(const C *__restrict__ M, bool ok, C &m00, C &m01, C &m10, C &m11) {
+    m00 = M[0]; m01 = M[1]; m10 = M[2]; m11 = M[3];
+    if (!ok) {
+        m00.x = 1; m00.y = 0; m01.x = 0; m01.y = 0; m10.x = 0; m10.y = 0; m11.x = 1; m11.y = 0;
     }
-    __device__ __forceinline__ void apply(double2 &a0, double2 &a1) const {
-        const double2 t0 = a0, t1 = a1;
-        double2 r0 = cmul(m00, t0); cfma(r0, m01, t1);
-        double2 r1 = cmul(m10, t0); cfma(r1, m11, t1);
-        a0 = r0; a1 = r1;
-    }
-};
-template <> struct Coef<float> {
-    float2 a00, b00, a01, b01, a10, b10, a11, b11;     // a = (mr, mr), b = (-mi, mi)
-    __device__ __forceinline__ void load(const float2 *__restrict__ M, bool ok) {
-        float2 m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
-        if (!ok) { m00 = make_float2(1.f, 0.f); m01 = make_float2(0.f, 0.f); m10 = make_float2(0.f, 0.f); m11 = make_float2(1.f, 0.f); }
-        a00 = make_float2(m00.x, m00.x); b00 = make_float2(-m00.y, m00.y);
-        a01 = make_float2(m01.x, m01.x); b01 = make_float2(-m01.y, m01.y);
-        a10 = make_float2(m10.x, m10.x); b10 = make_float2(-m10.y, m10.y);
-        a11 = make_float2(m11.x, m11.x); b11 = make_float2(-m11.y, m11.y);
-    }
-    __device__ __forceinline__ void apply(float2 &a0, float2 &a1) const {
-        const float2 t0 = a0, t1 = a1;
-        const float2 s0 = make_float2(t0.y, t0.x), s1 = make_float2(t1.y, t1.x);
-        float2 r0 = __fmul2_rn(a00, t0);
-        r0 = __ffma2_rn(b00, s0, r0); r0 = __ffma2_rn(a01, t1, r0); r0 = __ffma2_rn(b01, s1, r0);
-        float2 r1 = __fmul2_rn(a10, t0);
-        r1 = __ffma2_rn(b10, s0, r1); r1 = __ffma2_rn(a11, t1, r1); r1 = __ffma2_rn(b11, s1, r1);
-        a0 = r0; a1 = r1;
-    }
-};
-// phase multiplication d * a
-__device__ __forceinline__ double2 phase_mul(const double2 d, const double2 a) { return cmul(d, a); }
-__device__ __forceinline__ float2 phase_mul(const float2 d, const float2 a) {
-    const float2 s = make_float2(a.y, a.x);
-    return __ffma2_rn(make_float2(-d.y, d.y), s, __fmul2_rn(make_float2(d.x, d.x), a));
 }
 template <typename C> __device__ __forceinline__ C load_phase(const C *__restrict__ M, bool ok) {
     C d = M[0];
@@ -161,33 +146,36 @@ template <typename C> __device__ __forceinline__ C load_phase(const C *__restric
     return d;
 }
 
-// 2x2 gate on register bit J, no register-bit control
 template <typename R, int NX, int J, int FORM>
 __device__ __forceinline__ void u1_free(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M, bool ok) {
-    Coef<R> c;
-    c.load(M, ok);
+    using C = typename CxT<R>::T;
+    C m00, m01, m10, m11;
+    load_matrix(M, ok, m00, m01, m10, m11);
 #pragma unroll
     for (int x0 = 0; x0 < NX; ++x0)
-        if (!(x0 & (1 << J))) c.apply(a[x0], a[x0 | (1 << J)]);
+        if (!(x0 & (1 << J))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
 }
 // ... controlled by register bit CB (must be 1)
 template <typename R, int NX, int J, int CB, int FORM>
 __device__ __forceinline__ void u1_ctrl(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M, bool ok) {
-    Coef<R> c;
-    c.load(M, ok);
+    using C = typename CxT<R>::T;
+    C m00, m01, m10, m11;
+    load_matrix(M, ok, m00, m01, m10, m11);
 #pragma unroll
     for (int x0 = 0; x0 < NX; ++x0)
-        if (!(x0 & (1 << J)) && (x0 & (1 << CB))) c.apply(a[x0], a[x0 | (1 << J)]);
+        if (!(x0 & (1 << J)) && (x0 & (1 << CB))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
 }
 // ... any register-bit control pattern, checked per pair (uniform across the CTA)
 template <typename R, int NX, int J>
 __device__ __forceinline__ void u1_masked(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
                                           uint32_t rc, uint32_t rv, bool ok) {
-    Coef<R> c;
-    c.load(M, ok);
+    using C = typename CxT<R>::T;
+    C m00, m01, m10, m11;
+    load_matrix(M, ok, m00, m01, m10, m11);
 #pragma unroll
     for (int x0 = 0; x0 < NX; ++x0)
-        if (!(x0 & (1 << J)) && ((uint32_t)x0 & rc) == rv) c.apply(a[x0], a[x0 | (1 << J)]);
+        if (!(x0 & (1 << J)) && ((uint32_t)x0 & rc) == rv)
+            butterfly<R, U1_GENERAL>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
 }
 // phase on the amplitudes whose register bits in MASK are all 1
 template <typename R, int NX, int MASK, int FORM>
@@ -196,7 +184,7 @@ __device__ __forceinline__ void phase_bits(typename CxT<R>::T (&a)[NX], const ty
     for (int x = 0; x < NX; ++x)
         if ((x & MASK) == MASK) {
             if (FORM == PHASE_NEG) { a[x].x = -a[x].x; a[x].y = -a[x].y; }
-            else a[x] = phase_mul(d, a[x]);
+            else a[x] = cmul(d, a[x]);
         }
 }
 
@@ -235,12 +223,12 @@ __device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], type
         case ARM_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv, ok); break;
         QCS_PH1(0) QCS_PH1(1) QCS_PH1(2) QCS_PH1(3)
         QCS_PH2(0, 0, 1) QCS_PH2(1, 0, 2) QCS_PH2(2, 0, 3) QCS_PH2(3, 1, 2) QCS_PH2(4, 1, 3) QCS_PH2(5, 2, 3)
-        case ARM_PHT: ph = phase_mul(load_phase(M, ok), ph); break;
+        case ARM_PHT: ph = cmul(load_phase(M, ok), ph); break;
         default: {   // ARM_PHG
             const C d = load_phase(M, ok);
 #pragma unroll
             for (uint32_t x = 0; x < (uint32_t)NX; ++x)
-                if ((x & rc) == rv) a[x] = phase_mul(d, a[x]);
+                if ((x & rc) == rv) a[x] = cmul(d, a[x]);
         } break;
     }
 #undef QCS_U1F_J
@@ -312,7 +300,7 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, co
         }
         if (sw.thread_phase) {
 #pragma unroll
-            for (uint32_t x = 0; x < NX; ++x) a[x] = phase_mul(ph, a[x]);
+            for (uint32_t x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
         }
         if (VEC) {
 #pragma unroll
