@@ -40,6 +40,7 @@ PROTOTYPES = {
                                c_void_p, c_void_p]),
     'qcs_apply_dense': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    'qcs_plan_stats': (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     'qcs_apply_fused': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     'qcs_abs2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

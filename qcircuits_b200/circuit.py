@@ -34,7 +34,7 @@ class _Gate:
         self.nd_mask = 0 if plan.diagonal else tmask
         self.d_mask = cmask | (tmask if plan.diagonal else 0)
         t = len(plan.targets)
-        self.entries = (1 << t) if plan.diagonal else (1 << (2 * t))
+        self.entries = (2 << t) if plan.diagonal else (1 << (2 * t))
         self.wide = t > _lib.QCS_MAX_OP_QUBITS
 
 
@@ -107,12 +107,24 @@ def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None):
     return passes
 
 
+def _cheap_form(M):
+    """True if the tile engine has a cheap register body for the 2x2 matrix M (qcs_tile.cu arm table):
+    diagonal (a phase), real (H, RY, X, Z ...) or real diagonal with imaginary off-diagonal (RX, Y)."""
+    if M[0, 1] == 0 and M[1, 0] == 0:
+        return True
+    if not M.imag.any():
+        return True
+    return M[0, 0].imag == 0 and M[1, 1].imag == 0 and M[0, 1].real == 0 and M[1, 0].real == 0
+
+
 def merge_single_qubit_gates(gates):
     """Peephole fusion before scheduling: an uncontrolled one-qubit gate waits in a per-bit accumulator;
     later one-qubit gates on the same bit multiply into it, gates that act *diagonally* on the bit
     (controls, diagonal targets) are let through while the accumulator is itself diagonal (they commute),
-    and anything else flushes it.  So RZ / S / T slide through CZ and CNOT controls into the next H or RX
-    and disappear as separate ops.  Returns a new gate list (same unitary up to rounding)."""
+    and anything else flushes it.  Two gates are multiplied only while the product keeps a cheap register
+    body (diagonal, real, RX-like: RZ.RZ, RX.RX, H.RY ...); H.RZ would be a general complex 2x2 that costs
+    more instructions than H and the phase separately.  Returns a new gate list (same unitary up to
+    rounding)."""
     from . import _gates
     out = []
     acc = {}          # bit -> 2x2 matrix
@@ -130,7 +142,14 @@ def merge_single_qubit_gates(gates):
         if not g.wide and len(plan.targets) == 1 and not plan.controls:
             b = g.bits[plan.targets[0]]
             M = np.diag(plan.matrix) if plan.diagonal else plan.matrix
-            acc[b] = M @ acc[b] if b in acc else np.array(M, dtype=np.complex128)
+            M = np.array(M, dtype=np.complex128)
+            if b in acc:
+                prod = M @ acc[b]
+                if _cheap_form(prod):
+                    acc[b] = prod
+                    continue
+                flush(b)        # the product would need the general complex 2x2 body: keep the two cheap ops
+            acc[b] = M
             continue
         nd = g.nd_mask
         for b in list(acc):

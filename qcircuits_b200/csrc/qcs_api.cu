@@ -80,6 +80,12 @@ int qcs_tile_limits(int dtype, int *low_bits, int *tile_bits) {
     return QCS_OK;
 }
 
+int qcs_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats) {
+    if (!ops || !stats) return set_error(QCS_ERR_ARG, "null argument");
+    if (nops < 1 || nops > QCS_MAX_OPS) return set_error(QCS_ERR_ARG, "nops must be in 1..QCS_MAX_OPS");
+    return tile_plan_stats(n, dtype, ops, nops, stats);
+}
+
 int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
                     double *norm_out, void *ws, qcs_stream stream) {
     if (int e = check_state(dst, n, dtype)) return e;

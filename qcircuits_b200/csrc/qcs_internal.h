@@ -38,17 +38,13 @@ struct TileOp {
 };
 
 // register-level ops of a sweep
-constexpr int REGOP_U1 = 0;      // 2x2 matrix on register bit j
-constexpr int REGOP_PHASE = 1;   // multiply the amplitudes whose index matches (care, val) by one complex number
-constexpr int U1_GENERAL = 0, U1_REAL = 1, U1_RXLIKE = 2, U1_ANTIDIAG = 3, U1_SWAP = 4;
-constexpr int PHASE_GENERAL = 0, PHASE_NEG = 1;
-constexpr int MAX_OUTER_PREDS = 64;
+constexpr int MAX_OUTER_PREDS = 63;      // slot 63 of the per-tile predicate mask means "no predicate"
 struct RegOp {                   // 16 bytes, read with one 128-bit shared-memory load
-    uint16_t code;               // kind | j << 2 | form << 4
+    uint16_t code;               // arm of the interpreter (gen_regops.py)
     uint8_t reg_care, reg_val;   // masks over the sweep's register bits
     uint16_t base_care, base_val;// tile-local index bits that are not register bits (per-thread predicate)
-    int32_t mat;                 // pool offset (U1: 4 entries row-major, PHASE: 1)
-    int32_t outer_slot;          // -1, or index of the tile-uniform predicate this op depends on
+    int32_t mat;                 // byte offset of the op's coefficients in the pool (16-byte aligned)
+    int32_t outer_slot;          // index of the tile-uniform predicate this op depends on, 63 = none
 };
 struct OuterPred { uint64_t care, val; };   // flat-index bits outside the tile
 constexpr int SWEEP_REG = 0, SWEEP_GENERIC = 1;
@@ -88,6 +84,8 @@ int set_error(int code, const char *msg);
 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
                double *norm_out, void *ws, cudaStream_t stream);
+
+int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
 
 int misc_set_basis(void *buf, int n, int dtype, uint64_t index, cudaStream_t st);
 int misc_abs2(double *probs, const void *src, int n, int dtype, const double *norm_in, double *sum_out, void *ws,

@@ -103,139 +103,20 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 // ------------------------------------------------------------------------------------------------
 // register sweeps
 // ------------------------------------------------------------------------------------------------
-// Register-op bodies.  Every position that selects registers (target bit J, register control bit CB,
-// phase bits) is a template parameter, so a body is straight-line arithmetic on named registers with no
-// per-amplitude predicate; the class id of an op (RegOp::code) picks the body through one jump table.
-// Controls that are not register bits are one per-thread predicate around the whole body.
-template <typename R, int FORM>
-__device__ __forceinline__ void butterfly(typename CxT<R>::T &a0, typename CxT<R>::T &a1, const typename CxT<R>::T m00,
-                                          const typename CxT<R>::T m01, const typename CxT<R>::T m10,
-                                          const typename CxT<R>::T m11) {
-    using C = typename CxT<R>::T;
-    const C t0 = a0, t1 = a1;
-    C r0, r1;
-    if (FORM == U1_REAL) {
-        r0.x = fma(m00.x, t0.x, m01.x * t1.x); r0.y = fma(m00.x, t0.y, m01.x * t1.y);
-        r1.x = fma(m10.x, t0.x, m11.x * t1.x); r1.y = fma(m10.x, t0.y, m11.x * t1.y);
-    } else if (FORM == U1_RXLIKE) {   // real diagonal, imaginary off-diagonal
-        r0.x = fma(m00.x, t0.x, -m01.y * t1.y); r0.y = fma(m00.x, t0.y, m01.y * t1.x);
-        r1.x = fma(m11.x, t1.x, -m10.y * t0.y); r1.y = fma(m11.x, t1.y, m10.y * t0.x);
-    } else if (FORM == U1_SWAP) {
-        r0 = t1; r1 = t0;
-    } else {
-        r0 = cmul(m00, t0); cfma(r0, m01, t1);
-        r1 = cmul(m10, t0); cfma(r1, m11, t1);
-    }
-    a0 = r0; a1 = r1;
-}
-
-// 2x2 gate on register bit J, no register-bit control
-// Coefficients of an op for this thread: the op's own when its per-thread / per-tile predicate holds, the
-// identity otherwise.  Substituting coefficients instead of branching keeps the op loop free of divergent
-// regions (the register allocator otherwise copies all 2^RB amplitudes into and out of every region).
-template <typename C>
-__device__ __forceinline__ void load_matrix(const C *__restrict__ M, bool ok, C &m00, C &m01, C &m10, C &m11) {
-    m00 = M[0]; m01 = M[1]; m10 = M[2]; m11 = M[3];
-    if (!ok) {
-        m00.x = 1; m00.y = 0; m01.x = 0; m01.y = 0; m10.x = 0; m10.y = 0; m11.x = 1; m11.y = 0;
-    }
-}
-template <typename C> __device__ __forceinline__ C load_phase(const C *__restrict__ M, bool ok) {
-    C d = M[0];
-    if (!ok) { d.x = 1; d.y = 0; }
-    return d;
-}
-
-template <typename R, int NX, int J, int FORM>
-__device__ __forceinline__ void u1_free(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M, bool ok) {
-    using C = typename CxT<R>::T;
-    C m00, m01, m10, m11;
-    load_matrix(M, ok, m00, m01, m10, m11);
-#pragma unroll
-    for (int x0 = 0; x0 < NX; ++x0)
-        if (!(x0 & (1 << J))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
-}
-// ... controlled by register bit CB (must be 1)
-template <typename R, int NX, int J, int CB, int FORM>
-__device__ __forceinline__ void u1_ctrl(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M, bool ok) {
-    using C = typename CxT<R>::T;
-    C m00, m01, m10, m11;
-    load_matrix(M, ok, m00, m01, m10, m11);
-#pragma unroll
-    for (int x0 = 0; x0 < NX; ++x0)
-        if (!(x0 & (1 << J)) && (x0 & (1 << CB))) butterfly<R, FORM>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
-}
-// ... any register-bit control pattern, checked per pair (uniform across the CTA)
-template <typename R, int NX, int J>
-__device__ __forceinline__ void u1_masked(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T *__restrict__ M,
-                                          uint32_t rc, uint32_t rv, bool ok) {
-    using C = typename CxT<R>::T;
-    C m00, m01, m10, m11;
-    load_matrix(M, ok, m00, m01, m10, m11);
-#pragma unroll
-    for (int x0 = 0; x0 < NX; ++x0)
-        if (!(x0 & (1 << J)) && ((uint32_t)x0 & rc) == rv)
-            butterfly<R, U1_GENERAL>(a[x0], a[x0 | (1 << J)], m00, m01, m10, m11);
-}
-// phase on the amplitudes whose register bits in MASK are all 1
-template <typename R, int NX, int MASK, int FORM>
-__device__ __forceinline__ void phase_bits(typename CxT<R>::T (&a)[NX], const typename CxT<R>::T d) {
-#pragma unroll
-    for (int x = 0; x < NX; ++x)
-        if ((x & MASK) == MASK) {
-            if (FORM == PHASE_NEG) { a[x].x = -a[x].x; a[x].y = -a[x].y; }
-            else a[x] = cmul(d, a[x]);
-        }
-}
-
-// arm ids (RegOp::code), dense so that the dispatch is one jump table
-constexpr int ARM_U1F = 0;      // + j                              (4)  2x2 on register bit j
-constexpr int ARM_U1C = 4;      // + j * 3 + rank of cb among != j   (12) ... controlled by register bit cb
-constexpr int ARM_U1G = 16;     // + j                              (4)  ... any register-bit control pattern
-constexpr int ARM_PH1 = 20;     // + j                              (4)  phase where register bit j is 1
-constexpr int ARM_PH2 = 24;     // + pair(j1 < j2)                  (6)  phase where both bits are 1
-constexpr int ARM_PHT = 30;     // phase uniform over the thread's amplitudes
-constexpr int ARM_PHG = 31;     // phase on any (care, value) pattern over the register bits
-__host__ __device__ constexpr int u1c_arm(int j, int cb) { return ARM_U1C + j * 3 + (cb < j ? cb : cb - 1); }
-
-template <typename R, int RB>
-__device__ __forceinline__ void run_regop(typename CxT<R>::T (&a)[1 << RB], typename CxT<R>::T &ph, int cls,
-                                          const typename CxT<R>::T *__restrict__ M, uint32_t rc, uint32_t rv, bool ok) {
-    using C = typename CxT<R>::T;
-    constexpr int NX = 1 << RB;
-    // All arithmetic forms share one body per register position: with ~30 arms ptxas keeps the 2^RB
-    // amplitudes in place across the switch; with one arm per (position, form) it copied all of them into
-    // and out of every arm (ncu: MOV = 27 % of the instructions of a fused pass, ALU pipe 62 % busy).
-#define QCS_U1F_J(J) case ARM_U1F + (J): if ((J) < RB) u1_free<R, NX, ((J) < RB ? (J) : 0), U1_GENERAL>(a, M, ok); break;
-#define QCS_U1C(J, CB) \
-    case u1c_arm(J, CB): if ((J) < RB && (CB) < RB) u1_ctrl<R, NX, ((J) < RB ? (J) : 0), ((CB) < RB ? (CB) : 1), U1_GENERAL>(a, M, ok); break;
-#define QCS_PH1(J) \
-    case ARM_PH1 + (J): if ((J) < RB) phase_bits<R, NX, (1 << ((J) < RB ? (J) : 0)), PHASE_GENERAL>(a, load_phase(M, ok)); break;
-#define QCS_PH2(P, J1, J2) \
-    case ARM_PH2 + (P): if ((J2) < RB) phase_bits<R, NX, ((J2) < RB ? ((1 << (J1)) | (1 << (J2))) : 1), PHASE_GENERAL>(a, load_phase(M, ok)); break;
-    switch (cls) {
-        QCS_U1F_J(0) QCS_U1F_J(1) QCS_U1F_J(2) QCS_U1F_J(3)
-        QCS_U1C(0, 1) QCS_U1C(0, 2) QCS_U1C(0, 3) QCS_U1C(1, 0) QCS_U1C(1, 2) QCS_U1C(1, 3)
-        QCS_U1C(2, 0) QCS_U1C(2, 1) QCS_U1C(2, 3) QCS_U1C(3, 0) QCS_U1C(3, 1) QCS_U1C(3, 2)
-        case ARM_U1G + 0: u1_masked<R, NX, 0>(a, M, rc, rv, ok); break;
-        case ARM_U1G + 1: if (1 < RB) u1_masked<R, NX, (1 < RB ? 1 : 0)>(a, M, rc, rv, ok); break;
-        case ARM_U1G + 2: if (2 < RB) u1_masked<R, NX, (2 < RB ? 2 : 0)>(a, M, rc, rv, ok); break;
-        case ARM_U1G + 3: if (3 < RB) u1_masked<R, NX, (3 < RB ? 3 : 0)>(a, M, rc, rv, ok); break;
-        QCS_PH1(0) QCS_PH1(1) QCS_PH1(2) QCS_PH1(3)
-        QCS_PH2(0, 0, 1) QCS_PH2(1, 0, 2) QCS_PH2(2, 0, 3) QCS_PH2(3, 1, 2) QCS_PH2(4, 1, 3) QCS_PH2(5, 2, 3)
-        case ARM_PHT: ph = cmul(load_phase(M, ok), ph); break;
-        default: {   // ARM_PHG
-            const C d = load_phase(M, ok);
-#pragma unroll
-            for (uint32_t x = 0; x < (uint32_t)NX; ++x)
-                if ((x & rc) == rv) a[x] = cmul(d, a[x]);
-        } break;
-    }
-#undef QCS_U1F_J
-#undef QCS_U1C
-#undef QCS_PH1
-#undef QCS_PH2
-}
+// A fused pass is instruction-issue-bound, so the op interpreter is written for the fewest instructions
+// per op (gen_regops.py -> qcs_regops.inc, one inline-PTX block per amplitude type):
+//  * dispatch is one `brx.idx` through a jump table (a C++ switch became a 6-level compare/branch tree and
+//    the compiler copied all 2^RB loop-carried amplitudes between two register sets once per op);
+//  * all arithmetic is an in-place real 2x2 map on a pair of registers; gates are classified on the host
+//    into the cheapest exact form, and common scalar factors (1/sqrt2 of H, cos of RX) are deferred into the
+//    pass-level factor that the final store applies anyway;
+//  * every position that selects registers (target bit, control bit, phase bits) is baked into the arm.
+// Instructions per thread (complex64, 16 amplitudes): HAD 32, REALU / IMAGU 48, REAL / IMAG 64, GEN 128,
+// PH1 32, SGN1 16, PH2 16, SGN2 8, CX 24 (moves), PHT 4; + ~8 per op for fetch and dispatch.
+// Predicates that do not involve register bits (control bits elsewhere in the tile / outside the tile) are
+// the "_P" entries: they substitute identity coefficients instead of branching around the body.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#include "qcs_regops.inc"
 
 // MT > 0: the tile has exactly MT bits, every sweep uses RB register bits (compile-time trip counts).
 template <typename R, int RB, typename Layout, int MT>
@@ -257,8 +138,7 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, co
         ps[j] = j < nreg ? Layout::amp(1u << rp[j]) : 0u;
     }
     const uint32_t ngroups = 1u << (m - nreg);
-    const int nops = sw.count;
-    const uint4 *ops4 = reinterpret_cast<const uint4 *>(rops + sw.first);
+    const uint32_t ops_smem = smem_u32(rops + sw.first), pool_smem = smem_u32(pool);
 #pragma unroll
     for (uint32_t g = tid; g < ngroups; g += nt) {
         uint32_t base = g;
@@ -276,6 +156,10 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, co
             addr[x] = o;
         }
         C a[NX];
+        if (!FAST) {
+#pragma unroll
+            for (uint32_t x = 0; x < NX; ++x) a[x] = cx<R>(R(0), R(0));     // slots beyond 2^nreg stay defined
+        }
         if (VEC) {
 #pragma unroll
             for (uint32_t x = 0; x < NX; x += 2) {
@@ -290,14 +174,7 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, co
                 if (FAST || x < nx_used) a[x] = tile[addr[x]];
         }
         C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
-        for (int o = 0; o < nops; ++o) {
-            const uint4 w = ops4[o];                         // one broadcast 128-bit load per op
-            const int slot = (int)w.w;
-            const bool tile_ok = slot < 0 || ((outer_ok >> slot) & 1ull);        // tile-uniform predicate
-            const uint32_t bcare = w.y & 0xffffu, bval = w.y >> 16;
-            const bool ok = tile_ok && (base & bcare) == bval;                   // per-thread predicate
-            run_regop<R, RB>(a, ph, (int)(w.x & 0xffffu), pool + (int)w.z, (w.x >> 16) & 0xffu, w.x >> 24, ok);
-        }
+        run_sweep_ops(a, ph, ops_smem, pool_smem, base, outer_ok);
         if (sw.thread_phase) {
 #pragma unroll
             for (uint32_t x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
@@ -400,7 +277,8 @@ __device__ __forceinline__ void run_program(typename CxT<R>::T *tile, const Prog
     using C = typename CxT<R>::T;
     constexpr int RB = sizeof(C) == 8 ? REG_BITS_C64 : REG_BITS_C128;
     const C *pool = reinterpret_cast<const C *>(pv.pool);
-    const uint64_t outer_ok = pv.nouter ? pv.outer_ok[parity] : 0ull;
+    // bit OUTER_SLOT_NONE is always set: ops without a tile-level predicate name that slot
+    const uint64_t outer_ok = (pv.nouter ? pv.outer_ok[parity] : 0ull) | (1ull << OUTER_SLOT_NONE);
     for (int s = 0; s < pv.nsweeps; ++s) {
         const Sweep &sw = pv.sweeps[s];
         if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout, MT>(tile, m, sw, pv.regops, pool, outer_ok, tid, nt);
@@ -440,7 +318,6 @@ template <> __device__ __forceinline__ uint4 vec_scale<double>(const uint4 v, do
     return r;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------------------------------------
 // Variant 0: cp.async ring, padded layout, every warp both copies and computes
@@ -809,7 +686,8 @@ struct HostOp {            // one entry of the caller's list, classified
 
 template <typename Prog>
 static int build_and_launch(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
-                            const double *norm_in, double *norm_out, void *ws, cudaStream_t stream) {
+                            const double *norm_in, double *norm_out, void *ws, cudaStream_t stream,
+                            int32_t *stats = nullptr) {
     const bool c64 = dtype == QCS_C64;
     const int vshift = c64 ? 1 : 0;
     Prog *Pp = new Prog();
@@ -898,6 +776,28 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         used += entries;
         return at;
     };
+    // `count` reals, 16-byte aligned (read with 128-bit shared-memory loads); returns the entry index
+    auto push_reals = [&](const double *v, int count) -> int {
+        const size_t per = c64 ? 2 : 1;                          // entries per 16 bytes
+        used = (used + per - 1) / per * per;
+        const size_t entries = c64 ? (size_t)(count + 1) / 2 : (size_t)(count + 1) / 2;
+        const size_t padded = (entries + per - 1) / per * per;
+        if (used + padded > pool_cap) return -1;
+        const int at = (int)used;
+        if (c64) {
+            float *p = reinterpret_cast<float *>(P.mats) + 2 * used;
+            for (size_t e = 0; e < 2 * padded; ++e) p[e] = e < (size_t)count ? (float)v[e] : 0.0f;
+        } else {
+            double *p = reinterpret_cast<double *>(P.mats) + 2 * used;
+            for (size_t e = 0; e < 2 * padded; ++e) p[e] = e < (size_t)count ? v[e] : 0.0;
+        }
+        used += padded;
+        return at;
+    };
+    auto gphase_mul = [&](double re, double im) {
+        const double gr = P.gphase[0] * re - P.gphase[1] * im, gi = P.gphase[0] * im + P.gphase[1] * re;
+        P.gphase[0] = gr; P.gphase[1] = gi;
+    };
 
     // ---- sweeps: greedy, commuting ops may overtake ops that wait for a later sweep --------------------
     const int rb = c64 ? REG_BITS_C64 : REG_BITS_C128;
@@ -969,7 +869,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         }
         // flat-index (care, val) -> register / thread / tile parts of a RegOp; false if out of slots
         auto split_masks = [&](uint64_t care, uint64_t val, RegOp &r) -> bool {
-            r.reg_care = r.reg_val = 0; r.base_care = r.base_val = 0; r.outer_slot = -1;
+            r.reg_care = r.reg_val = 0; r.base_care = r.base_val = 0; r.outer_slot = OUTER_SLOT_NONE;
             const uint64_t oc = care & ~tile_mask, ov = val & ~tile_mask;
             if (oc) {
                 int slot = -1;
@@ -998,20 +898,60 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         };
         for (int t = 0; t < ntaken; ++t) {
             const qcs_op &o = ops[taken[t]];
+            if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
             if (hop[taken[t]].kind == 0) {
-                if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
                 RegOp &r = P.regops[P.nregops++];
                 const int j = reg_index_of_local[local_of(o.bitpos[0])];
                 const double *M = o.matrix;   // m00 m01 m10 m11 as (re, im)
                 if (!split_masks(o.ctrl_mask, o.ctrl_mask, r))
                     return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
+                // the cheapest exact form of the matrix (arm table: gen_regops.py)
                 const int nrc = __builtin_popcount(r.reg_care);
-                if (nrc == 0) r.code = (uint16_t)(ARM_U1F + j);
-                else if (nrc == 1) r.code = (uint16_t)u1c_arm(j, __builtin_ctz(r.reg_care));
-                else r.code = (uint16_t)(ARM_U1G + j);
-                const int at = push_entries(M, 4);
-                if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
-                r.mat = at;
+                const bool free_op = o.ctrl_mask == 0;
+                const bool pred = r.base_care != 0 || r.outer_slot != OUTER_SLOT_NONE;
+                const bool real = M[1] == 0.0 && M[3] == 0.0 && M[5] == 0.0 && M[7] == 0.0;
+                const bool imag = M[1] == 0.0 && M[7] == 0.0 && M[2] == 0.0 && M[4] == 0.0;   // real diagonal, imaginary off-diagonal
+                const bool is_x = real && M[0] == 0.0 && M[6] == 0.0 && M[2] == 1.0 && M[4] == 1.0;
+                double cf[8];
+                int ncf = 0;
+                if (nrc == 1 && is_x && !pred) {
+                    r.code = (uint16_t)cx_arm(j, __builtin_ctz(r.reg_care));
+                } else if (nrc >= 1) {
+                    r.code = (uint16_t)(ARM_GENM + j);
+                    for (int e = 0; e < 8; ++e) cf[e] = M[e];
+                    ncf = 8;
+                } else if (free_op && real && M[0] != 0.0 && M[0] == M[2] && M[0] == M[4] && M[0] == -M[6]) {
+                    r.code = (uint16_t)(ARM_HAD + j);
+                    gphase_mul(M[0], 0.0);
+                } else if (free_op && real && M[0] != 0.0 && M[0] == M[6] && fabs(M[2]) <= 2.0 * fabs(M[0]) &&
+                           fabs(M[4]) <= 2.0 * fabs(M[0])) {
+                    r.code = (uint16_t)(ARM_REALU + j);
+                    cf[0] = M[2] / M[0]; cf[1] = M[4] / M[0]; ncf = 2;
+                    gphase_mul(M[0], 0.0);
+                } else if (free_op && imag && M[0] != 0.0 && M[0] == M[6] && fabs(M[3]) <= 2.0 * fabs(M[0]) &&
+                           fabs(M[5]) <= 2.0 * fabs(M[0])) {
+                    // out0 = a0 + i b a1, out1 = a1 + i g a0 (b = Im m01 / m00, g = Im m10 / m00):
+                    // (re a0, im a1) -> (u - b v, v + g u)
+                    r.code = (uint16_t)(ARM_IMAGU + j);
+                    cf[0] = -M[3] / M[0]; cf[1] = M[5] / M[0]; ncf = 2;
+                    gphase_mul(M[0], 0.0);
+                } else if (real) {
+                    r.code = (uint16_t)((pred ? ARM_REAL_P : ARM_REAL) + j);
+                    cf[0] = M[0]; cf[1] = M[2]; cf[2] = M[4]; cf[3] = M[6]; ncf = 4;
+                } else if (imag) {
+                    r.code = (uint16_t)((pred ? ARM_IMAG_P : ARM_IMAG) + j);
+                    cf[0] = M[0]; cf[1] = -M[3]; cf[2] = M[5]; cf[3] = M[6]; ncf = 4;
+                } else {
+                    r.code = (uint16_t)((pred ? ARM_GEN_P : ARM_GEN) + j);
+                    for (int e = 0; e < 8; ++e) cf[e] = M[e];
+                    ncf = 8;
+                }
+                r.mat = 0;
+                if (ncf) {
+                    const int at = push_reals(cf, ncf);
+                    if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
+                    r.mat = at * (int)csize;          // byte offset into the pool
+                }
                 ++sw.count;
             } else {
                 // diagonal on k bits.  An uncontrolled diagonal is d[0] * diag(1, d[x]/d[0], ...): the common
@@ -1020,8 +960,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 if (o.ctrl_mask == 0 && !(o.matrix[0] == 1.0 && o.matrix[1] == 0.0) &&
                     (o.matrix[0] != 0.0 || o.matrix[1] != 0.0)) {
                     d0r = o.matrix[0]; d0i = o.matrix[1];
-                    const double gr = P.gphase[0] * d0r - P.gphase[1] * d0i, gi = P.gphase[0] * d0i + P.gphase[1] * d0r;
-                    P.gphase[0] = gr; P.gphase[1] = gi;
+                    gphase_mul(d0r, d0i);
                 }
                 const double d0n = d0r * d0r + d0i * d0i;
                 for (int x = 0; x < (1 << o.k); ++x) {
@@ -1042,33 +981,54 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     if (!split_masks(care, val, r))
                         return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
                     const int nrc = __builtin_popcount(r.reg_care);
+                    const bool pred = r.base_care != 0 || r.outer_slot != OUTER_SLOT_NONE;
+                    const bool all_ones = r.reg_val == r.reg_care, is_real = im == 0.0;
+                    static const int pair_index[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+                    double cf[4] = {re, -im, im, re};       // the factor as a real 2x2 map on (re, im)
+                    int ncf = 4;
                     if (nrc == 0) {
                         r.code = (uint16_t)ARM_PHT;
                         sw.thread_phase = 1;
-                    } else if (nrc == 1 && r.reg_val == r.reg_care) {
-                        r.code = (uint16_t)(ARM_PH1 + __builtin_ctz(r.reg_care));
-                    } else if (nrc == 2 && r.reg_val == r.reg_care) {
+                    } else if (nrc == 1 && all_ones) {
+                        const int jj = __builtin_ctz(r.reg_care);
+                        r.code = (uint16_t)((is_real ? (pred ? ARM_SGN1_P : ARM_SGN1) : (pred ? ARM_PH1_P : ARM_PH1)) + jj);
+                        if (is_real) ncf = 1;
+                    } else if (nrc == 2 && all_ones) {
                         const int j1 = __builtin_ctz(r.reg_care), j2 = 31 - __builtin_clz((unsigned)r.reg_care);
-                        static const int pair_index[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
-                        r.code = (uint16_t)(ARM_PH2 + pair_index[j1][j2]);
+                        const int pi = pair_index[j1][j2];
+                        r.code = (uint16_t)((is_real ? (pred ? ARM_SGN2_P : ARM_SGN2) : (pred ? ARM_PH2_P : ARM_PH2)) + pi);
+                        if (is_real) ncf = 1;
                     } else {
-                        r.code = (uint16_t)ARM_PHG;
+                        r.code = (uint16_t)ARM_PHM;
                     }
-                    const double d[2] = {re, im};
-                    const int at = push_entries(d, 1);
+                    const int at = push_reals(cf, ncf);
                     if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
-                    r.mat = at;
+                    r.mat = at * (int)csize;
                     ++sw.count;
                 }
             }
         }
-        if (sw.count > 0) ++P.nsweeps;     // (a run of exact identities produces no work)
+        if (sw.count > 0) {                // (a run of exact identities produces no work)
+            if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
+            RegOp &endop = P.regops[P.nregops++];          // terminates the interpreter loop of this sweep
+            endop.code = (uint16_t)ARM_END; endop.reg_care = endop.reg_val = 0; endop.base_care = endop.base_val = 0;
+            endop.mat = 0; endop.outer_slot = OUTER_SLOT_NONE;
+            ++P.nsweeps;
+        }
         for (int i = 0; i < nrest; ++i) pending[i] = rest[i];
         npend = nrest;
     }
     P.mat_bytes = (int32_t)(used * csize);
-    const bool has_gphase = !(P.gphase[0] == 1.0 && P.gphase[1] == 0.0);
-    P.scale_mode = has_gphase ? 2 : (norm_in ? 1 : 0);
+    // 2: complex factor, 1: real factor (lazy norm and / or deferred real scalars), 0: none
+    P.scale_mode = P.gphase[1] != 0.0 ? 2 : ((norm_in || P.gphase[0] != 1.0) ? 1 : 0);
+    if (stats) {       // planning only (qcs_plan_stats): tile bits, sweeps, register ops, per-arm counts
+        stats[0] = m; stats[1] = P.nsweeps; stats[2] = P.nregops; stats[3] = P.ngen; stats[4] = P.nouter;
+        stats[5] = P.scale_mode;
+        for (int i = 0; i < 120; ++i) stats[8 + i] = 0;
+        for (int i = 0; i < P.nregops; ++i)
+            if (P.regops[i].code < 120) stats[8 + P.regops[i].code]++;
+        return QCS_OK;
+    }
     const DeviceInfo &dev = device_info();
     const int mode = tile_mode();
     return c64 ? launch_tile<float, Prog>(P, dev, mode, stream) : launch_tile<double, Prog>(P, dev, mode, stream);
@@ -1082,6 +1042,11 @@ int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, 
         if (rc != QCS_ERR_UNSUPPORTED) return rc;
     }
     return build_and_launch<LargeProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
+}
+
+int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats) {
+    if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
+    return build_and_launch<LargeProg>(nullptr, nullptr, n, dtype, ops, nops, nullptr, nullptr, nullptr, nullptr, stats);
 }
 
 }  // namespace qcs
