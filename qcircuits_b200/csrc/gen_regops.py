@@ -53,12 +53,11 @@ class Gen:
         self.emit('fma.rn.%s %s, %s, %s, m2_%d;' % (self.ty, v, s, v, t))
         self.temps.add(('m1_%d' % t)); self.temps.add(('m2_%d' % t))
 
-    def map2u(self, u, v, q, r):
-        t = self.tmp()
-        self.emit('mul.%s m2_%d, %s, %s;' % (self.ty, t, r, u))
+    def map2u(self, u, v, q, r, d):
+        """u' = u + q v ; v' = v + r u = d v + r u' with d = 1 - r q (no copy of the old u is needed)"""
         self.emit('fma.rn.%s %s, %s, %s, %s;' % (self.ty, u, q, v, u))
-        self.emit('add.%s %s, %s, m2_%d;' % (self.ty, v, v, t))
-        self.temps.add('m2_%d' % t)
+        self.emit('mul.%s %s, %s, %s;' % (self.ty, v, v, d))
+        self.emit('fma.rn.%s %s, %s, %s, %s;' % (self.ty, v, r, u, v))
 
     def addsub(self, u, v):
         m2 = '0fC0000000' if self.ty == 'f32' else '0dC000000000000000'
@@ -103,11 +102,12 @@ class Gen:
 
     def compute_ok(self):
         e = self.emit
-        e('and.b32 t0, w1, 0xffff;')
-        e('shr.u32 t1, w1, 16;')
+        e('ld.shared.v4.u32 {k0, k1, k2, k3}, [opa+-32];')     # this op's record (w* already hold the next one)
+        e('and.b32 t0, k1, 0xffff;')
+        e('shr.u32 t1, k1, 16;')
         e('and.b32 t2, %%%d, t0;' % self.BASE)
         e('setp.eq.u32 ok, t2, t1;')
-        e('shr.u64 tt, %%%d, w3;' % self.OUTER)
+        e('shr.u64 tt, %%%d, k3;' % self.OUTER)
         e('cvt.u32.u64 t3, tt;')
         e('and.b32 t3, t3, 1;')
         e('setp.ne.u32 pt, t3, 0;')
@@ -124,8 +124,8 @@ class Gen:
         e('selp.%s c3, c3, %s, ok;' % (self.ty, self.one()))
 
     def rcrv(self):
-        self.emit('bfe.u32 rc, w0, 16, 8;')
-        self.emit('shr.u32 rv, w0, 24;')
+        self.emit('bfe.u32 rc, k0, 16, 8;')
+        self.emit('shr.u32 rv, k0, 24;')
 
     def done_arm(self):
         self.emit('bra.uni L_NEXT;')
@@ -160,7 +160,6 @@ class Gen:
             for j in J:
                 if j >= rb: absent('REAL'); continue
                 self.arm('A_REAL%s%d' % ('P' if pred else '', j))
-                self.cfaddr(); self.ld4()
                 if pred:
                     self.compute_ok(); self.sel_identity4()
                     self.emit('bra.uni B_REAL%d;' % j)
@@ -176,16 +175,14 @@ class Gen:
         for j in J:
             if j >= rb: absent('REALU'); continue
             self.arm('A_REALU%d' % j)
-            self.cfaddr(); self.ld2()
             for x0, x1 in self.pairs(j):
-                self.map2u(self.re(x0), self.re(x1), 'c0', 'c1'); self.map2u(self.im(x0), self.im(x1), 'c0', 'c1')
+                self.map2u(self.re(x0), self.re(x1), 'c0', 'c1', 'c2'); self.map2u(self.im(x0), self.im(x1), 'c0', 'c1', 'c2')
             self.done_arm()
         # IMAG
         def imag_family(pred):
             for j in J:
                 if j >= rb: absent('IMAG'); continue
                 self.arm('A_IMAG%s%d' % ('P' if pred else '', j))
-                self.cfaddr(); self.ld4()
                 if pred:
                     self.compute_ok(); self.sel_identity4()
                     self.emit('bra.uni B_IMAG%d;' % j)
@@ -202,14 +199,13 @@ class Gen:
         for j in J:
             if j >= rb: absent('IMAGU'); continue
             self.arm('A_IMAGU%d' % j)
-            self.cfaddr(); self.ld2()
             self.emit('neg.%s n1, c0;' % ty); self.emit('neg.%s n3, c1;' % ty)
             for x0, x1 in self.pairs(j):
-                self.map2u(self.re(x0), self.im(x1), 'c0', 'c1'); self.map2u(self.im(x0), self.re(x1), 'n1', 'n3')
+                self.map2u(self.re(x0), self.im(x1), 'c0', 'c1', 'c2'); self.map2u(self.im(x0), self.re(x1), 'n1', 'n3', 'c2')
             self.done_arm()
         # GEN (plain / predicated)
         def gen_coefs(pred):
-            self.cfaddr(); self.ld4(); self.ld4(('c4', 'c5', 'c6', 'c7'), 4 * self.esz)
+            self.ld4(('c4', 'c5', 'c6', 'c7'), 4 * self.esz)
             if pred:
                 e = self.emit
                 for r, idv in (('c0', self.one()), ('c1', self.zero()), ('c2', self.zero()), ('c3', self.zero()),
@@ -263,7 +259,6 @@ class Gen:
             for k, mask in enumerate(masks):
                 if mask is None: absent(tag); continue
                 self.arm('A_%s%s%d' % (tag, 'P' if pred else '', k))
-                self.cfaddr(); self.ld4()
                 if pred:
                     self.compute_ok(); self.sel_identity4()
                     self.emit('bra.uni B_%s%d;' % (tag, k))
@@ -277,7 +272,6 @@ class Gen:
             for k, mask in enumerate(masks):
                 if mask is None: absent(tag); continue
                 self.arm('A_%s%s%d' % (tag, 'P' if pred else '', k))
-                self.cfaddr(); self.ld1()
                 if pred:
                     self.compute_ok()
                     self.emit('selp.%s c0, c0, %s, ok;' % (ty, self.one()))
@@ -298,12 +292,12 @@ class Gen:
         sign_family('SGN2', m2, False); sign_family('SGN2', m2, True)
         # PHT: thread-uniform phase (always predicated: a uniform unpredicated phase is the pass-level factor)
         self.arm('A_PHT')
-        self.cfaddr(); self.ld4(); self.compute_ok(); self.sel_identity4()
+        self.compute_ok(); self.sel_identity4()
         self.map2('%%%d' % self.PH[0], '%%%d' % self.PH[1], 'c0', 'c1', 'c2', 'c3')
         self.done_arm()
         # PHM: phase on any (care, value) pattern over the register bits
         self.arm('A_PHM')
-        self.cfaddr(); self.ld4(); self.compute_ok(); self.sel_identity4(); self.rcrv()
+        self.compute_ok(); self.sel_identity4(); self.rcrv()
         for x in range(nx):
             t = self.tmp()
             self.emit('and.b32 t0, rc, %d;' % x)
@@ -323,7 +317,7 @@ class Gen:
         body = self.build()
         ty = self.ty
         head = []
-        head.append('.reg .b32 w0, w1, w2, w3, cls, cf, opa, t0, t1, t2, t3, rc, rv;')
+        head.append('.reg .b32 w0, w1, w2, w3, k0, k1, k2, k3, cls, cf, opa, t0, t1, t2, t3, rc, rv;')
         head.append('.reg .b64 tt;')
         head.append('.reg .pred ok, pt;')
         head.append('.reg .%s c0, c1, c2, c3, c4, c5, c6, c7, n1, n3, n5, n7, sw;' % ty)
@@ -331,13 +325,24 @@ class Gen:
         for i in range(0, len(temps), 8):
             head.append('.reg .%s %s;' % (ty, ', '.join(temps[i:i + 8])))
         targets = ', '.join(self.labels)
+        # software pipeline: the record of op i+1 is fetched while op i runs; the first four coefficients of
+        # op i are fetched in the head (every arm but HAD / CX / END uses them) so that their latency overlaps
+        # the jump-table load and the indirect branch
         head.append('mov.u32 opa, %%%d;' % self.OPS)
-        head.append('L_NEXT:')
         head.append('ld.shared.v4.u32 {w0, w1, w2, w3}, [opa];')
         head.append('add.u32 opa, opa, 16;')
+        head.append('L_NEXT:')
         head.append('and.b32 cls, w0, 0xffff;')
+        head.append('add.u32 cf, w2, %%%d;' % self.POOL)
+        head.append('ld.shared.v4.u32 {w0, w1, w2, w3}, [opa];')
+        head.append('add.u32 opa, opa, 16;')
+        if ty == 'f32':
+            head.append('ld.shared.v4.f32 {c0, c1, c2, c3}, [cf];')
+        else:
+            head.append('ld.shared.v2.f64 {c0, c1}, [cf];')
+            head.append('ld.shared.v2.f64 {c2, c3}, [cf+16];')
         head.append('TBL: .branchtargets %s;' % targets)
-        head.append('brx.idx cls, TBL;')
+        head.append('brx.idx.uni cls, TBL;')
         tail = ['L_DONE:']
         out = []
         out.append('__device__ __forceinline__ void run_sweep_ops(%s (&a)[%d], %s &ph, uint32_t ops_smem, uint32_t pool_smem,'

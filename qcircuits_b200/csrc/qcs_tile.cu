@@ -112,7 +112,8 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 //    pass-level factor that the final store applies anyway;
 //  * every position that selects registers (target bit, control bit, phase bits) is baked into the arm.
 // Instructions per thread (complex64, 16 amplitudes): HAD 32, REALU / IMAGU 48, REAL / IMAG 64, GEN 128,
-// PH1 32, SGN1 16, PH2 16, SGN2 8, CX 24 (moves), PHT 4; + ~8 per op for fetch and dispatch.
+// PH1 32, SGN1 16, PH2 16, SGN2 8, CX 24 (moves), PHT 4; + ~9 per op for fetch and dispatch.  The loop is
+// software-pipelined: the record of op i+1 and the coefficients of op i are in flight during the dispatch.
 // Predicates that do not involve register bits (control bits elsewhere in the tile / outside the tile) are
 // the "_P" entries: they substitute identity coefficients instead of branching around the body.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -926,14 +927,14 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 } else if (free_op && real && M[0] != 0.0 && M[0] == M[6] && fabs(M[2]) <= 2.0 * fabs(M[0]) &&
                            fabs(M[4]) <= 2.0 * fabs(M[0])) {
                     r.code = (uint16_t)(ARM_REALU + j);
-                    cf[0] = M[2] / M[0]; cf[1] = M[4] / M[0]; ncf = 2;
+                    cf[0] = M[2] / M[0]; cf[1] = M[4] / M[0]; cf[2] = 1.0 - cf[0] * cf[1]; ncf = 3;
                     gphase_mul(M[0], 0.0);
                 } else if (free_op && imag && M[0] != 0.0 && M[0] == M[6] && fabs(M[3]) <= 2.0 * fabs(M[0]) &&
                            fabs(M[5]) <= 2.0 * fabs(M[0])) {
                     // out0 = a0 + i b a1, out1 = a1 + i g a0 (b = Im m01 / m00, g = Im m10 / m00):
                     // (re a0, im a1) -> (u - b v, v + g u)
                     r.code = (uint16_t)(ARM_IMAGU + j);
-                    cf[0] = -M[3] / M[0]; cf[1] = M[5] / M[0]; ncf = 2;
+                    cf[0] = -M[3] / M[0]; cf[1] = M[5] / M[0]; cf[2] = 1.0 - cf[0] * cf[1]; ncf = 3;
                     gphase_mul(M[0], 0.0);
                 } else if (real) {
                     r.code = (uint16_t)((pred ? ARM_REAL_P : ARM_REAL) + j);
