@@ -10,6 +10,7 @@ identical to applying the gates one by one (up to floating-point reassociation o
 normalisation) and is checked against the oracle in tests/.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -45,20 +46,41 @@ def tile_limits(dtype):
     return low.value, tile.value
 
 
-def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None):
-    """Greedy fusion: repeatedly pick the tile (low bits + a window of high bits) that admits the most
-    pending gates, where a gate may overtake an earlier one only if they commute (they share no bit on
-    which either acts non-diagonally).  ``gates`` are records with nd_mask / d_mask / entries / wide over
-    the n flat bits of the (local) state.  Returns lists of indices into ``gates``."""
+def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None, low_shrink=None):
+    """Greedy fusion: repeatedly pick the tile that admits the most pending gates, where a gate may overtake
+    an earlier one only if they commute (they share no bit on which either acts non-diagonally).  A tile is
+    the low L flat bits plus a window of H consecutive higher bits with L + H = tile_bits; L ranges from the
+    engine's preferred contiguous run down to ``low_shrink`` bits less (a shorter contiguous run buys a wider
+    window: for nearest-neighbour circuits the gates a window absorbs grow with the square of its width).
+    ``gates`` are records with nd_mask / d_mask / entries / wide over the n flat bits of the (local) state.
+    Returns lists of indices into ``gates``."""
     low, tile = tile_limits(dtype)
-    L = min(low, n)
-    hcap = max(0, min(tile - low if high_bits is None else high_bits, n - L))
-    low_mask = (1 << L) - 1
+    if low_shrink is None:
+        low_shrink = int(os.environ.get('QCS_LOW_SHRINK', '3'))
+    geoms = []
+    if high_bits is not None:
+        geoms.append((min(low, n), max(0, min(high_bits, n - min(low, n)))))
+    else:
+        for shrink in range(0, low_shrink + 1):
+            L = min(low - shrink, n)
+            geoms.append((L, max(0, min(tile - L, n - L))))
+            if L == n:
+                break
+    L0 = geoms[0][0]
     pool_cap = 12288 // (8 if np.dtype(dtype) == np.complex64 else 16) - 4
     max_ops = min(max_ops, _lib.QCS_MAX_OPS)
     remaining = list(range(len(gates)))
     passes = []
     full = (1 << n) - 1
+    candidates = []
+    for L, hcap in geoms:
+        low_mask = (1 << L) - 1
+        if low_mask not in candidates:
+            candidates.append(low_mask)
+        for s in range(L, n - hcap + 1):
+            mask = low_mask | (((1 << hcap) - 1) << s)
+            if mask not in candidates:
+                candidates.append(mask)
 
     def scan(tile_mask):
         blk_nd = blk_d = 0
@@ -82,19 +104,18 @@ def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None):
         if first.wide:                      # operator wider than the tile engine: its own dense pass
             passes.append([remaining.pop(0)])
             continue
-        candidates = [low_mask]
-        for s in range(L, n - hcap + 1):
-            candidates.append(low_mask | (((1 << hcap) - 1) << s))
+        cands = candidates
         # the first pending gate must always be schedulable: its own high bits, padded upwards
+        low_mask, hcap = (1 << L0) - 1, geoms[0][1]
         need = first.nd_mask & ~low_mask
         if need and bin(need).count('1') <= hcap:
-            m, b = need, L
+            m, b = need, L0
             while bin(m).count('1') < hcap and b < n:
                 m |= 1 << b
                 b += 1
-            candidates.append(low_mask | m)
+            cands = candidates + [low_mask | m]
         best = None
-        for mask in candidates:
+        for mask in cands:
             taken = scan(mask)
             if best is None or len(taken) > len(best):
                 best = taken

@@ -215,7 +215,7 @@ template <typename Prog>
 static uint32_t program_smem_bytes(const Prog &P) {
     return align128(align16(P.nsweeps * (uint32_t)sizeof(Sweep)) + align16(P.nregops * (uint32_t)sizeof(RegOp)) +
                     align16(P.nouter * (uint32_t)sizeof(OuterPred)) + align16(P.ngen * (uint32_t)sizeof(TileOp)) +
-                    align16((uint32_t)P.mat_bytes) + 16u + (uint32_t)sizeof(uint64_t) * (1u << P.H));
+                    align16((uint32_t)P.mat_bytes) + 16u + (uint32_t)sizeof(uint64_t) * ((1u << P.H) + 8u));
 }
 
 __device__ __forceinline__ void copy_words(void *dst, const void *src, uint32_t bytes, int tid, int nt) {
@@ -255,6 +255,18 @@ __device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Pro
     }
     chunk_off = co;
     o += (uint32_t)sizeof(uint64_t) * (1u << P.H);
+    // flat offsets of the 8 combinations of the top three tile bits (compile-time-geometry staging loops)
+    uint64_t *hi = reinterpret_cast<uint64_t *>(smem + o);
+    if (tid < 8) {
+        const int mt = P.L + P.H;
+        uint64_t off = 0;
+        for (int j = 0; j < 3; ++j) {
+            const int i = mt - 3 + j;
+            if (i >= 0 && ((tid >> j) & 1)) off |= 1ull << (i < P.L ? i : P.hbits[i - P.L]);
+        }
+        hi[tid] = off;
+    }
+    o += (uint32_t)sizeof(uint64_t) * 8u;
     pv.nsweeps = P.nsweeps;
     pv.nouter = P.nouter;
     return align128(o);
@@ -378,7 +390,6 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
     using Layout = PaddedLayout<C>;
     constexpr bool FAST = MT > 0;
     constexpr int NT = PipeThreads<R, MT>::value;
-    constexpr int LSTD = sizeof(C) == 8 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
     constexpr int VSHIFT = sizeof(C) == 8 ? 1 : 0;       // amplitudes per 16-byte vector = 1 << VSHIFT
     extern __shared__ __align__(128) unsigned char smem_all[];
     const int tid = threadIdx.x;
@@ -386,16 +397,17 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
     ProgView pv;
     const uint64_t *chunk_off;
     const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, nt);
+    const uint64_t *hi_off = chunk_off + (1u << P.H);     // the 8 offsets of the top three tile bits
     unsigned char *ring = smem_all + prog_bytes;
-    const int L = FAST ? LSTD : P.L;
+    const int L = P.L;
     const int m = FAST ? MT : P.L + P.H;
     const int S = P.stages;
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(m);
     const uint32_t nchunks = 1u << (m - L);
     const uint32_t chunk_vecs = (1u << L) >> VSHIFT;     // 16-byte vectors per contiguous chunk
     const uint32_t chunk_svecs = Layout::vec(chunk_vecs);// ... and their padded extent in shared memory
-    // this thread's vectors inside a chunk: w = tid, tid + nt, ... ; the padded map is additive over
-    // the disjoint bit ranges of tid and the stride, so both addresses advance by constants
+    // this thread's vectors: v = tid, tid + nt, ... ; the padded map is additive over the disjoint bit
+    // ranges of tid and the stride, so the shared-memory address advances by a constant
     const uint32_t svec_tid = Layout::vec((uint32_t)tid);
     const uint32_t svec_step = Layout::vec((uint32_t)nt);
     const int scale_mode = P.scale_mode;                 // 0 none, 1 real, 2 complex
@@ -404,25 +416,46 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
         const double s = load_inv_norm(P.norm_in);
         fr = (R)(s * P.gphase[0]); fi = (R)(s * P.gphase[1]);
     }
-    const uint4 *src = reinterpret_cast<const uint4 *>(P.src) + tid;
-    uint4 *dst = reinterpret_cast<uint4 *>(P.dst) + tid;
+    // Compile-time geometry: the tile has 8 * NT vectors; vector v = tid + k * NT has its low bits from tid
+    // and its top three tile bits from k.  Tile bit i sits at flat bit i (i < L) or hbits[i - L], so the
+    // flat offset of a vector is (tile base) + (a per-thread constant) + (one of 8 per-pass constants),
+    // whatever the split between contiguous low bits and high bits (L is a run-time property of the pass).
+    constexpr int NK = 8;
+    uint64_t low_tid = 0;
+    if (FAST) {
+        for (int b = 0; b < MT - 3 - VSHIFT; ++b)
+            if ((tid >> b) & 1) {
+                const int i = b + VSHIFT;
+                low_tid |= 1ull << (i < L ? i : P.hbits[i - L]);
+            }
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.src) + (FAST ? (low_tid >> VSHIFT) : (uint64_t)tid);
+    uint4 *dst = reinterpret_cast<uint4 *>(P.dst) + (FAST ? (low_tid >> VSHIFT) : (uint64_t)tid);
     double nacc[1] = {0.0};
     const uint64_t my_tiles = (P.ntiles > blockIdx.x) ? (P.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    __syncthreads();   // program + chunk table visible
+    __syncthreads();   // program + offset tables visible
 
     auto issue_load = [&](uint64_t it, int st) {
         const uint64_t base = tile_base_of(blockIdx.x + it * gridDim.x, P);
         const uint32_t stage_u32 = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
+        if (FAST) {
+            uint32_t sp = stage_u32;
 #pragma unroll
-        for (uint32_t c = 0; c < nchunks; ++c) {
-            const uint4 *gp = src + ((base + chunk_off[c]) >> VSHIFT);
-            uint32_t sp = stage_u32 + c * chunk_svecs * 16u;
-#pragma unroll
-            for (uint32_t w = 0; w < chunk_vecs; w += nt) {
-                if (FAST || w + tid < chunk_vecs)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
-                gp += nt;
+            for (int k = 0; k < NK; ++k) {
+                const uint4 *gp = src + ((base + hi_off[k]) >> VSHIFT);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
                 sp += svec_step * 16u;
+            }
+        } else {
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                const uint4 *gp = src + ((base + chunk_off[c]) >> VSHIFT);
+                uint32_t sp = stage_u32 + c * chunk_svecs * 16u;
+                for (uint32_t w = 0; w < chunk_vecs; w += nt) {
+                    if (w + tid < chunk_vecs)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+                    gp += nt;
+                    sp += svec_step * 16u;
+                }
             }
         }
     };
@@ -445,21 +478,25 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
         // stream the tile out: fold the lazy scale / global phase, accumulate the squared norm
         R tacc = R(0);
         const uint4 *sbase = reinterpret_cast<const uint4 *>(stage) + svec_tid;
+        auto emit = [&](const uint4 *sp, uint4 *gp) {
+            uint4 val = *sp;
+            if (scale_mode == 1) val = vec_scale<R>(val, fr);
+            else if (scale_mode == 2) val = vec_cscale<R>(val, fr, fi);
+            vec_norm_acc(tacc, val, R(0));
+            *gp = val;
+        };
+        if (FAST) {
 #pragma unroll
-        for (uint32_t c = 0; c < nchunks; ++c) {
-            uint4 *gp = dst + ((base + chunk_off[c]) >> VSHIFT);
-            const uint4 *sp = sbase + c * chunk_svecs;
-#pragma unroll
-            for (uint32_t w = 0; w < chunk_vecs; w += nt) {
-                if (FAST || w + tid < chunk_vecs) {
-                    uint4 val = *sp;
-                    if (scale_mode == 1) val = vec_scale<R>(val, fr);
-                    else if (scale_mode == 2) val = vec_cscale<R>(val, fr, fi);
-                    vec_norm_acc(tacc, val, R(0));
-                    *gp = val;
+            for (int k = 0; k < NK; ++k) emit(sbase + k * svec_step, dst + ((base + hi_off[k]) >> VSHIFT));
+        } else {
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                uint4 *gp = dst + ((base + chunk_off[c]) >> VSHIFT);
+                const uint4 *sp = sbase + c * chunk_svecs;
+                for (uint32_t w = 0; w < chunk_vecs; w += nt) {
+                    if (w + tid < chunk_vecs) emit(sp, gp);
+                    gp += nt;
+                    sp += svec_step;
                 }
-                gp += nt;
-                sp += svec_step;
             }
         }
         nacc[0] += (double)tacc;
@@ -632,7 +669,7 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
     } else {
         constexpr int MSTD = sizeof(C) == 8 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
         constexpr int LSTD = sizeof(C) == 8 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
-        const bool fast_ok = P.L == LSTD && tune_int("QCS_PIPE_GENERIC", 0) == 0;
+        const bool fast_ok = tune_int("QCS_PIPE_GENERIC", 0) == 0;
         int ctas = tune_int("QCS_PIPE_CTAS", 2);
         if (ctas < 1) ctas = 1;
         if (ctas > 2) ctas = 2;

@@ -49,7 +49,8 @@ def test_schedule_is_a_valid_reordering(dtype):
     want = _run_oracle(c, range(len(c)), vec)
     got = _run_oracle(c, order, vec)
     assert np.max(np.abs(got - want)) < 1e-12
-    # every pass fits a tile: dense targets above the low bits number at most tile - low
+    # every pass fits a tile: for some contiguous low run L (the engine shrinks it down from `low`), the
+    # dense targets above bit L number at most tile - L
     low, tile = (10, 13) if dtype == np.complex64 else (9, 12)
     for p in passes:
         if len(p) == 1:
@@ -57,7 +58,7 @@ def test_schedule_is_a_valid_reordering(dtype):
         nd = 0
         for i in p:
             nd |= c.gates[i].nd_mask
-        assert bin(nd >> low).count('1') <= tile - low
+        assert any(bin(nd >> L).count('1') <= tile - L for L in range(low - 3, low + 1))
 
 
 def test_headline_circuit_fuses_well():
