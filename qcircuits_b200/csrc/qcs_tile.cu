@@ -119,6 +119,59 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 #include "qcs_regops.inc"
 
+// Compile-time geometry (MT tile bits, 2^(MT - RB) threads): exactly one group of 2^RB amplitudes per thread
+// and sweep.  The zero insertions and the byte strides come precomputed in the Sweep record, so the 2^RB
+// shared-memory addresses cost ~27 integer instructions (they were 80 when derived from the bit positions).
+template <typename R, int RB, typename Layout>
+__device__ __forceinline__ void reg_sweep_fast(typename CxT<R>::T *tile, const Sweep &sw, const RegOp *rops,
+                                               const typename CxT<R>::T *pool, uint64_t outer_ok, int tid) {
+    using C = typename CxT<R>::T;
+    constexpr int NX = 1 << RB;
+    const bool VEC = sizeof(C) == 8 && sw.rpos[0] == 0;     // complex64 pairs move as one 128-bit access
+    uint32_t base = (uint32_t)tid;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) base += base & sw.himask[j];
+    const uint32_t tile_u32 = smem_u32(tile) + Layout::amp(base) * (uint32_t)sizeof(C);
+    uint32_t addr[NX];
+    addr[0] = tile_u32;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        const uint32_t st = sw.stride[j];
+#pragma unroll
+        for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st;
+    }
+    C a[NX];
+    if (VEC) {
+#pragma unroll
+        for (int x = 0; x < NX; x += 2)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(reinterpret_cast<float &>(a[x].x)), "=f"(reinterpret_cast<float &>(a[x].y)),
+                           "=f"(reinterpret_cast<float &>(a[x + 1].x)), "=f"(reinterpret_cast<float &>(a[x + 1].y))
+                         : "r"(addr[x])
+                         : "memory");
+    } else {
+#pragma unroll
+        for (int x = 0; x < NX; ++x) a[x] = *reinterpret_cast<const C *>(__cvta_shared_to_generic(addr[x]));
+    }
+    C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
+    run_sweep_ops(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
+    if (sw.thread_phase) {
+#pragma unroll
+        for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
+    }
+    if (VEC) {
+#pragma unroll
+        for (int x = 0; x < NX; x += 2)
+            asm volatile("st.shared.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(reinterpret_cast<float &>(a[x].x)),
+                         "f"(reinterpret_cast<float &>(a[x].y)), "f"(reinterpret_cast<float &>(a[x + 1].x)),
+                         "f"(reinterpret_cast<float &>(a[x + 1].y)), "r"(addr[x])
+                         : "memory");
+    } else {
+#pragma unroll
+        for (int x = 0; x < NX; ++x) *reinterpret_cast<C *>(__cvta_shared_to_generic(addr[x])) = a[x];
+    }
+}
+
 // MT > 0: the tile has exactly MT bits, every sweep uses RB register bits (compile-time trip counts).
 template <typename R, int RB, typename Layout, int MT>
 __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, const Sweep &sw, const RegOp *rops,
@@ -294,7 +347,10 @@ __device__ __forceinline__ void run_program(typename CxT<R>::T *tile, const Prog
     const uint64_t outer_ok = (pv.nouter ? pv.outer_ok[parity] : 0ull) | (1ull << OUTER_SLOT_NONE);
     for (int s = 0; s < pv.nsweeps; ++s) {
         const Sweep &sw = pv.sweeps[s];
-        if (sw.kind == SWEEP_REG) reg_sweep<R, RB, Layout, MT>(tile, m, sw, pv.regops, pool, outer_ok, tid, nt);
+        if (sw.kind == SWEEP_REG) {
+            if (MT > 0) reg_sweep_fast<R, RB, Layout>(tile, sw, pv.regops, pool, outer_ok, tid);
+            else reg_sweep<R, RB, Layout, MT>(tile, m, sw, pv.regops, pool, outer_ok, tid, nt);
+        }
         else apply_generic<R, Layout>(tile, m, pv.gen[sw.first], pool, tile_base, tid, nt);
         __syncthreads();
     }
@@ -897,10 +953,16 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             if (!(S_local & (1u << b))) { S_local |= 1u << b; ++S_count; }
         sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg; sw.thread_phase = 0;
         int8_t reg_index_of_local[32];
+        for (int j = 0; j < REG_BITS_MAX; ++j) { sw.rpos[j] = 0; sw.himask[j] = 0; sw.stride[j] = 0; }
         for (int b = 0, j = 0; b < 32; ++b) {
             reg_index_of_local[b] = -1;
             if ((S_local >> b) & 1u) {
-                if (j < REG_BITS_MAX) sw.rpos[j] = (int8_t)b;
+                if (j < REG_BITS_MAX) {
+                    sw.rpos[j] = (int8_t)b;
+                    sw.himask[j] = ~((1u << b) - 1u);
+                    sw.stride[j] = c64 ? (uint32_t)(PaddedLayout<float2>::amp(1u << b) * sizeof(float2))
+                                       : (uint32_t)(PaddedLayout<double2>::amp(1u << b) * sizeof(double2));
+                }
                 reg_index_of_local[b] = (int8_t)j;
                 ++j;
             }
