@@ -94,10 +94,16 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=12.0)
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--workload', default='layered', choices=['layered', 'qpe'],
+                    help='layered = the headline random circuit; qpe = BASELINE config 3 (phase estimation + inverse QFT)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.qubits is None:
         args.qubits = 30 if world == 1 else 33 + int(np.log2(world))
+    if args.workload == 'qpe':          # config 3 is a device-resident run; the CPU / host-buffer legs belong to the headline
+        args.skip_cpu = args.skip_e2e = True
+        if args.qubits is None or args.qubits == 30:
+            args.qubits = 32
     if args.impl == 'reference':
         return reference_arm(args)
     if world > 1:
@@ -113,12 +119,21 @@ def main():
     np_dtype = np.complex64 if args.dtype == 'c64' else np.complex128
     amp_bytes = 8 if args.dtype == 'c64' else 16
     t0 = time.perf_counter()
-    circ = layered_circuit(n, depth, seed=SEED)
+    qpe = None
+    if args.workload == 'qpe':
+        from qcircuits_b200.workloads import phase_estimation_circuit
+        circ, eigvec, phase = phase_estimation_circuit(n - 2, seed=SEED)
+        qpe = {'true_phase': phase}
+    else:
+        circ = layered_circuit(n, depth, seed=SEED)
     fuse = not args.no_fuse
     passes, ngates = circ.stats(np_dtype, fuse=fuse, max_ops=args.max_ops)
     plan_s = time.perf_counter() - t0
 
-    state0 = qc.zeros(n, dtype=np_dtype)
+    if qpe is None:
+        state0 = qc.zeros(n, dtype=np_dtype)
+    else:
+        state0 = qc.zeros(n - 2, dtype=np_dtype) * qc.State(eigvec.reshape(2, 2), dtype=np_dtype)
     for _ in range(args.warmup):
         out = circ.run(state0, fuse=fuse, max_ops=args.max_ops)
     torch.cuda.synchronize()
@@ -139,6 +154,10 @@ def main():
     peak, peak_src = measured_peak()
     # the per-gate path (Operator.__call__: one pass per gate, north_star "per gate pass"): the first two
     # layers of the same circuit, unfused, timed the same way
+    if qpe is not None:
+        k = min(12, n - 2)
+        ps = out._measurement_probabilities(list(range(k)))
+        qpe.update({'estimated_phase_%d_bits' % k: int(np.argmax(ps)) / 2.0 ** k, 'peak_probability': float(ps.max())})
     from qcircuits_b200.workloads import layered_gate_list, operator_for
     from qcircuits_b200.circuit import Circuit
     two_layers = Circuit(n)
@@ -196,7 +215,10 @@ def main():
         'metric': 'gates/s, random layered circuit', 'value': value, 'unit': 'gates/s', 'n_gpus': 1,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': 'layered H/RX/RZ+CNOT/CZ circuit, %d qubits, depth %d, seed %d, |0..0> input' % (n, depth, SEED),
+        'config': {'workload': ('layered H/RX/RZ+CNOT/CZ circuit, %d qubits, depth %d, seed %d, |0..0> input' % (n, depth, SEED)
+                                if qpe is None else
+                                'phase estimation of a seeded 2-qubit unitary, %d-qubit register + inverse QFT, %d qubits, seed %d'
+                                % (n - 2, n, SEED)),
                    'gates': ngates, 'passes_per_step': passes, 'fused': fuse, 'max_ops_per_pass': args.max_ops,
                    'l2': 'state (%.1f GiB) is far larger than L2; no flush needed' % (2 ** n * amp_bytes / 2 ** 30),
                    'plan_s': plan_s},
@@ -208,6 +230,10 @@ def main():
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': passes * args.steps,
         'clocks': clocks.summary(), 'step_ms': step_ms, 'norm_check': probs_sum,
     }
+    if qpe is not None:
+        line['qpe_check'] = qpe
+        line['metric'] = 'gates/s, phase estimation + inverse QFT'
+    line['roofline']['gate_equivalent_GBs'] = pass_bytes * ngates / (ms_per_step * 1e-3) / 1e9
     print(json.dumps(line))
 
 

@@ -138,6 +138,30 @@ def _cheap_form(M):
     return M[0, 0].imag == 0 and M[1, 1].imag == 0 and M[0, 1].real == 0 and M[1, 0].real == 0
 
 
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+_CNOT = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
+
+
+def expand_swaps(gates):
+    """Swap = CNOT(a,b) CNOT(b,a) CNOT(a,b), exactly (all three are permutations): as controlled-X ops the
+    swap runs in the register sweeps of a fused pass (moves only when both bits are register bits) instead
+    of as a dense two-qubit op through shared memory."""
+    from . import _gates
+    out = []
+    cnot = None
+    for g in gates:
+        p = g.plan
+        if (not g.wide and not p.diagonal and not p.controls and len(p.targets) == 2
+                and np.array_equal(p.matrix, _SWAP)):
+            if cnot is None:
+                cnot = _gates.analyze(_CNOT)
+            a, b = g.bits[p.targets[0]], g.bits[p.targets[1]]
+            out.extend([_Gate(None, [a, b], plan=cnot), _Gate(None, [b, a], plan=cnot), _Gate(None, [a, b], plan=cnot)])
+        else:
+            out.append(g)
+    return out
+
+
 def merge_single_qubit_gates(gates):
     """Peephole fusion before scheduling: an uncontrolled one-qubit gate waits in a per-bit accumulator;
     later one-qubit gates on the same bit multiply into it, gates that act *diagonally* on the bit
@@ -223,7 +247,7 @@ class Circuit:
         comp = self._plans.get(key)
         if comp is None:
             comp = []
-            gates = merge_single_qubit_gates(self.gates) if fuse else self.gates
+            gates = merge_single_qubit_gates(expand_swaps(self.gates)) if fuse else self.gates
             groups = (schedule_passes(gates, self.n, dtype, max_ops=max_ops) if fuse
                       else [[i] for i in range(len(gates))])
             for group in groups:

@@ -93,3 +93,24 @@ def test_single_qubit_merge_preserves_the_unitary():
         if g.plan.full is not None:
             got = orc.apply_matrix_flat(g.plan.full, got, g.bits, renorm=False)
     assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_swap_expansion_preserves_the_unitary():
+    from qcircuits_b200.circuit import expand_swaps
+    rng = np.random.default_rng(11)
+    n = 9
+    c = Circuit(n)
+    c.append(qc.Hadamard(), [2])
+    c.append(qc.Swap(), [2, 7])
+    c.append(qc.RotationX(0.4), [7])
+    c.append(qc.Swap(), [0, 1])
+    c.append(qc.CNOT(), [1, 8])
+    ex = expand_swaps(c.gates)
+    assert len(ex) == len(c.gates) + 4
+    vec = rand_state_vec(rng, n)
+    want, got = vec, vec
+    for g in c.gates:
+        want = orc.apply_matrix_flat(g.plan.full, want, g.bits, renorm=False)
+    for g in ex:
+        got = orc.apply_matrix_flat(g.plan.full, got, g.bits, renorm=False)
+    assert np.max(np.abs(got - want)) < 1e-14
