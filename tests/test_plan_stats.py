@@ -1,0 +1,50 @@
+"""CPU-only: the host planner of the tile engine (qcs_plan_stats plans a pass without launching it)."""
+import ctypes
+
+import numpy as np
+
+import qcircuits_b200  # noqa: F401  (package import must work without a GPU)
+from qcircuits_b200 import _gates, _lib
+from qcircuits_b200._device import make_ops
+
+H = np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2)
+X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+CNOT = np.eye(4, dtype=np.complex128)[[0, 1, 3, 2]]
+CZ = np.diag([1, 1, 1, -1]).astype(np.complex128)
+
+
+def _stats(n, dtype, gates):
+    lib = _lib.load()
+    ops, keep = make_ops([(_gates.analyze(M), bits, False) for M, bits in gates])
+    st = (ctypes.c_int32 * 128)()
+    _lib.check(lib.qcs_plan_stats(n, _lib.dtype_code(dtype), ops, len(ops), st))
+    return list(st)
+
+
+def test_cheapest_forms_are_chosen():
+    rx = lambda t: np.array([[np.cos(t / 2), -1j * np.sin(t / 2)], [-1j * np.sin(t / 2), np.cos(t / 2)]])
+    st = _stats(20, np.complex64, [(H, [0]), (rx(0.7), [1]), (CNOT, [0, 1]), (CZ, [0, 1]), (rx(3.0), [2])])
+    arms = {a: st[8 + a] for a in range(100) if st[8 + a]}
+    # register bits 0, 1, 2 (+ one filler): H -> HAD on position 0, RX -> IMAGU on position 1, CNOT(control bit 0,
+    # target bit 1) -> CX, CZ -> SGN2 on the pair (0, 1), RX(3.0) (|tan| > 2) -> IMAG on position 2, then END
+    assert arms == {0: 1, 24 + 1: 1, 40 + 1 * 3 + 0: 1, 80: 1, 16 + 2: 1, 94: 1}
+    assert st[1] == 1 and st[2] == 6          # one sweep, five ops + END
+    assert st[5] == 1                         # deferred real scalars (1/sqrt2, cos) -> real pass-level factor
+
+
+def test_controls_outside_the_tile_become_predicates():
+    st = _stats(24, np.complex64, [(CNOT, [23, 3]), (CZ, [22, 3])])
+    arms = {a for a in range(100) if st[8 + a]}
+    assert any(8 <= a < 12 for a in arms)      # REAL_P: X under a tile-level predicate
+    assert any(64 <= a < 68 for a in arms)     # SGN1_P
+    assert st[4] == 2                          # two distinct tile-level predicates
+
+
+def test_tile_shrinks_its_contiguous_run_for_many_high_targets():
+    # five dense targets above bit 10: the planner gives up two contiguous low bits (L = 8, H = 5)
+    st = _stats(26, np.complex64, [(H, [b]) for b in (12, 14, 16, 18, 20)])
+    assert st[0] == 13
+    lib = _lib.load()
+    ops, keep = make_ops([(_gates.analyze(H), [b], False) for b in range(10, 26)])
+    out = (ctypes.c_int32 * 128)()
+    assert lib.qcs_plan_stats(26, 0, ops, len(ops), out) == -3      # QCS_ERR_UNSUPPORTED: too many high bits
