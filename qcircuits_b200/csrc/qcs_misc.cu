@@ -15,6 +15,29 @@ struct BitList {
     int32_t sorted[64];  // ascending
 };
 
+struct BinMap {
+    int32_t nbits;           // index bits of the source
+    uint64_t contrib[40];    // outcome bit(s) contributed by index bit b (0 if b is not measured)
+};
+template <typename T> struct VecOf;
+template <> struct VecOf<float2> { static constexpr int VE = 2, LV = 1; };
+template <> struct VecOf<double2> { static constexpr int VE = 1, LV = 0; };
+template <> struct VecOf<double> { static constexpr int VE = 2, LV = 1; };
+constexpr int MS_VECS = 8;                          // vectors per thread and segment
+constexpr int MS_SEG_VECS = 256 * MS_VECS;          // 2048
+template <typename T> __device__ __forceinline__ void vec_probs(const uint4 v, double (&p)[2]);
+template <> __device__ __forceinline__ void vec_probs<float2>(const uint4 v, double (&p)[2]) {
+    const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z), d = __uint_as_float(v.w);
+    p[0] = (double)fmaf(a, a, b * b); p[1] = (double)fmaf(c, c, d * d);
+}
+template <> __device__ __forceinline__ void vec_probs<double2>(const uint4 v, double (&p)[2]) {
+    const double a = __hiloint2double(v.y, v.x), b = __hiloint2double(v.w, v.z);
+    p[0] = fma(a, a, b * b); p[1] = 0.0;
+}
+template <> __device__ __forceinline__ void vec_probs<double>(const uint4 v, double (&p)[2]) {
+    p[0] = __hiloint2double(v.y, v.x); p[1] = __hiloint2double(v.w, v.z);
+}
+
 static unsigned ew_grid(uint64_t work_items, int per_sm = 8) {
     const DeviceInfo &dev = device_info();
     uint64_t g = (work_items + EW_THREADS - 1) / EW_THREADS;
@@ -46,6 +69,29 @@ __global__ void __launch_bounds__(EW_THREADS) abs2_kernel(double *__restrict__ p
         const double p = cabs2(src[i]) * inv;
         if (probs) probs[i] = p;
         acc[0] += p;
+    }
+    if (sum_out) grid_sum_publish<1>(acc, ws, sum_out);
+}
+// same, one 16-byte vector (VE amplitudes) per thread and step, four steps in flight; N >= 2 amplitudes
+template <typename C>
+__global__ void __launch_bounds__(EW_THREADS) abs2_vec_kernel(double *__restrict__ probs, const C *__restrict__ src,
+                                                              uint64_t NV, const double *norm_in, double *sum_out,
+                                                              void *ws) {
+    constexpr int VE = VecOf<C>::VE;
+    const double inv = norm_in ? 1.0 / *norm_in : 1.0;
+    double acc[1] = {0.0};
+    const uint4 *vs = reinterpret_cast<const uint4 *>(src);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+#pragma unroll 4
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += stride) {
+        double p[2];
+        vec_probs<C>(__ldcs(vs + v), p);
+        p[0] *= inv; p[1] *= inv;
+        if (probs) {
+            if (VE == 2) reinterpret_cast<double2 *>(probs)[v] = make_double2(p[0], p[1]);
+            else probs[v] = p[0];
+        }
+        acc[0] += p[0] + p[1];
     }
     if (sum_out) grid_sum_publish<1>(acc, ws, sum_out);
 }
@@ -107,6 +153,101 @@ __global__ void __launch_bounds__(EW_THREADS) kron_kernel(C *__restrict__ dst, c
     if (norm_out) grid_sum_publish<1>(acc, ws, norm_out);
 }
 
+// kron with nb >= 1 (complex64: the two amplitudes of a 16-byte vector share the `a` factor) -- one vector
+// store per thread and step, arithmetic in the amplitude type
+template <typename R>
+__global__ void __launch_bounds__(EW_THREADS) kron_vec_kernel(typename CxT<R>::T *__restrict__ dst,
+                                                              const typename CxT<R>::T *__restrict__ a,
+                                                              const typename CxT<R>::T *__restrict__ b, int na, int nb,
+                                                              const double *norm_a, const double *norm_b,
+                                                              double *norm_out, void *ws) {
+    using C = typename CxT<R>::T;
+    constexpr int VE = VecOf<C>::VE, LV = VecOf<C>::LV;
+    const R s = (R)(load_inv_norm(norm_a) * load_inv_norm(norm_b));
+    const uint64_t NV = (1ull << (na + nb)) >> LV, maskb = (1ull << nb) - 1ull;
+    double acc[1] = {0.0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+#pragma unroll 4
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += stride) {
+        const uint64_t i = v << LV;
+        C x = a[i >> nb];
+        x.x *= s; x.y *= s;
+        C r[VE], yv[VE];
+        if (VE == 2) {      // the pair of `b` factors is one aligned 16-byte load
+            const float4 yy = *reinterpret_cast<const float4 *>(b + (i & maskb));
+            yv[0].x = yy.x; yv[0].y = yy.y; yv[VE - 1].x = yy.z; yv[VE - 1].y = yy.w;
+        } else {
+            yv[0] = b[i & maskb];
+        }
+        R part = R(0);
+#pragma unroll
+        for (int u = 0; u < VE; ++u) {
+            const C y = yv[u];
+            r[u] = cmul(x, y);
+            part += r[u].x * r[u].x + r[u].y * r[u].y;
+        }
+        if (VE == 2) {
+            float4 o;
+            o.x = (float)r[0].x; o.y = (float)r[0].y; o.z = (float)r[VE - 1].x; o.w = (float)r[VE - 1].y;
+            __stcs(reinterpret_cast<float4 *>(dst) + v, o);
+        } else {
+            dst[v] = r[0];
+        }
+        acc[0] += (double)part;
+    }
+    if (norm_out) grid_sum_publish<1>(acc, ws, norm_out);
+}
+
+// kron with a small left factor (na <= 6): a thread loads one 16-byte vector of `b` once and writes it times
+// every amplitude of `a`, so `b` is read once instead of 2^na times (it does not fit L2 for large states)
+template <typename R>
+__global__ void __launch_bounds__(EW_THREADS) kron_small_a_kernel(typename CxT<R>::T *__restrict__ dst,
+                                                                  const typename CxT<R>::T *__restrict__ a,
+                                                                  const typename CxT<R>::T *__restrict__ b, int na, int nb,
+                                                                  const double *norm_a, const double *norm_b,
+                                                                  double *norm_out, void *ws) {
+    using C = typename CxT<R>::T;
+    constexpr int VE = VecOf<C>::VE, LV = VecOf<C>::LV;
+    __shared__ C as[64];
+    const R s = (R)(load_inv_norm(norm_a) * load_inv_norm(norm_b));
+    const uint32_t NA = 1u << na;
+    if (threadIdx.x < NA) { C x = a[threadIdx.x]; x.x *= s; x.y *= s; as[threadIdx.x] = x; }
+    __syncthreads();
+    const uint64_t NVB = (1ull << nb) >> LV;
+    double acc[1] = {0.0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < NVB; v += stride) {
+        C yv[VE];
+        if (VE == 2) {
+            const float4 yy = __ldcs(reinterpret_cast<const float4 *>(b) + v);
+            yv[0].x = yy.x; yv[0].y = yy.y; yv[VE - 1].x = yy.z; yv[VE - 1].y = yy.w;
+        } else {
+            yv[0] = b[v];
+        }
+        R part = R(0);
+#pragma unroll 4
+        for (uint32_t ai = 0; ai < NA; ++ai) {
+            const C x = as[ai];
+            C r[VE];
+#pragma unroll
+            for (int u = 0; u < VE; ++u) {
+                r[u] = cmul(x, yv[u]);
+                part += r[u].x * r[u].x + r[u].y * r[u].y;
+            }
+            const uint64_t o = ((uint64_t)ai << (nb - LV)) + v;
+            if (VE == 2) {
+                float4 w;
+                w.x = (float)r[0].x; w.y = (float)r[0].y; w.z = (float)r[VE - 1].x; w.w = (float)r[VE - 1].y;
+                __stcs(reinterpret_cast<float4 *>(dst) + o, w);
+            } else {
+                dst[o] = r[0];
+            }
+        }
+        acc[0] += (double)part;
+    }
+    if (norm_out) grid_sum_publish<1>(acc, ws, norm_out);
+}
+
 // ---- permute_bits (state.py:117,162) --------------------------------------------------------------
 template <typename C>
 __global__ void __launch_bounds__(EW_THREADS) permute_kernel(C *__restrict__ dst, const C *__restrict__ src, int n,
@@ -116,6 +257,45 @@ __global__ void __launch_bounds__(EW_THREADS) permute_kernel(C *__restrict__ dst
         uint64_t j = 0;
         for (int b = 0; b < n; ++b) j |= ((i >> b) & 1ull) << bl.pos[b];
         dst[i] = src[j];
+    }
+}
+// Large states: the source index of destination element e = ((seg * 8 + j) * 256 + tid) * VE + u is an OR of
+// per-bit contributions, P(e) = Ps(seg) | Pj(j) | Pt(tid, u), so the n-step bit loop runs once per segment
+// instead of once per amplitude; the destination is written with 16-byte vectors, the source is read with
+// 16-byte vectors when flat bit 0 stays in place (complex64) and with 8-byte gathers otherwise.
+template <typename C>
+__global__ void __launch_bounds__(EW_THREADS) permute_stream_kernel(C *__restrict__ dst, const C *__restrict__ src,
+                                                                   const __grid_constant__ BinMap pm) {
+    constexpr int VE = VecOf<C>::VE, LV = VecOf<C>::LV;
+    const int tid = threadIdx.x;
+    uint64_t Pt = 0;
+    for (int k = 0; k < 8; ++k)
+        if ((tid >> k) & 1) Pt |= pm.contrib[k + LV];
+    const uint64_t p_u = LV ? pm.contrib[0] : 0ull;             // source offset of the second amplitude of a vector
+    const uint64_t pj0 = pm.contrib[8 + LV], pj1 = pm.contrib[9 + LV], pj2 = pm.contrib[10 + LV];
+    const int seg_shift = 11 + LV;
+    const uint64_t nseg = (1ull << pm.nbits) >> seg_shift;
+    const bool pair_contiguous = VE == 2 && p_u == 1ull;
+    for (uint64_t sgm = blockIdx.x; sgm < nseg; sgm += gridDim.x) {
+        uint64_t ps = 0;
+        for (int k = 0; k + seg_shift < pm.nbits; ++k)
+            if ((sgm >> k) & 1ull) ps |= pm.contrib[k + seg_shift];
+        const uint64_t base = ps | Pt;
+        uint4 *vd = reinterpret_cast<uint4 *>(dst) + sgm * (uint64_t)MS_SEG_VECS + tid;
+        uint4 val[MS_VECS];
+#pragma unroll
+        for (int j = 0; j < MS_VECS; ++j) {
+            const uint64_t e = base | ((j & 1) ? pj0 : 0ull) | ((j & 2) ? pj1 : 0ull) | ((j & 4) ? pj2 : 0ull);
+            if (VE == 1 || pair_contiguous) {
+                val[j] = *reinterpret_cast<const uint4 *>(src + e);
+            } else {
+                const uint2 lo = *reinterpret_cast<const uint2 *>(src + e);
+                const uint2 hi = *reinterpret_cast<const uint2 *>(src + (e | p_u));
+                val[j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MS_VECS; ++j) __stcs(vd + j * EW_THREADS, val[j]);
     }
 }
 
@@ -191,6 +371,99 @@ __global__ void __launch_bounds__(EW_THREADS) marginal_large_kernel(double *out,
     }
 }
 
+// Streaming marginal kernel for states of at least one segment (2048 16-byte vectors).  Element index
+// e = ((seg * 8 + j) * 256 + tid) * VE + u, and the outcome ("bin") of an index is an OR of per-bit
+// contributions, so bin(e) = Bs(seg) | Bj(j) | Bt(tid, u): Bt is a per-thread constant, Bj a compile-time
+// selection of three per-pass masks, Bs is recomputed once per segment.  A CTA owns a contiguous range of
+// segments; a thread keeps 8 * VE float64 accumulators (one per (j, u)) for as long as Bs does not change
+// and flushes them with atomics into the shared-memory histogram (<= 2^10 outcomes) or the global one.
+// Per element: one 16-byte load shared by VE elements, 2 FMA, 1 add -- the kernel is HBM-bound.
+template <typename T, bool SMALL>
+__global__ void __launch_bounds__(EW_THREADS) marginal_stream_kernel(double *out, const T *__restrict__ src,
+                                                                    const __grid_constant__ BinMap bm, int m,
+                                                                    const double *norm_in, double *hists, void *ws) {
+    constexpr int VE = VecOf<T>::VE, LV = VecOf<T>::LV;
+    extern __shared__ double hist[];
+    __shared__ int last_flag;
+    const uint32_t nbins = SMALL ? (1u << m) : 0u;
+    if (SMALL) {
+        for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) hist[b] = 0.0;
+        __syncthreads();
+    }
+    const int tid = threadIdx.x;
+    const double inv = norm_in ? 1.0 / *norm_in : 1.0;
+    uint64_t Bt[VE];
+#pragma unroll
+    for (int u = 0; u < VE; ++u) {
+        const uint32_t e = ((uint32_t)tid << LV) | (uint32_t)u;
+        uint64_t b = 0;
+        for (int k = 0; k < 8 + LV; ++k)
+            if ((e >> k) & 1u) b |= bm.contrib[k];
+        Bt[u] = b;
+    }
+    const uint64_t bj0 = bm.contrib[8 + LV], bj1 = bm.contrib[9 + LV], bj2 = bm.contrib[10 + LV];
+    const int seg_shift = 11 + LV;                              // element bits below the segment index
+    const uint64_t nseg = (1ull << bm.nbits) >> seg_shift;
+    const uint64_t s_begin = nseg * blockIdx.x / gridDim.x, s_end = nseg * (blockIdx.x + 1) / gridDim.x;
+    const uint4 *vsrc = reinterpret_cast<const uint4 *>(src) + tid;
+    double acc[MS_VECS][VE];
+#pragma unroll
+    for (int j = 0; j < MS_VECS; ++j)
+#pragma unroll
+        for (int u = 0; u < VE; ++u) acc[j][u] = 0.0;
+    uint64_t cur = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < MS_VECS; ++j) {
+            const uint64_t bj = ((j & 1) ? bj0 : 0ull) | ((j & 2) ? bj1 : 0ull) | ((j & 4) ? bj2 : 0ull);
+#pragma unroll
+            for (int u = 0; u < VE; ++u) {
+                if (acc[j][u] != 0.0) {
+                    const uint64_t bin = cur | bj | Bt[u];
+                    if (SMALL) atomicAdd(&hist[bin], acc[j][u]);
+                    else atomicAdd(&out[bin], acc[j][u] * inv);
+                    acc[j][u] = 0.0;
+                }
+            }
+        }
+    };
+    for (uint64_t sgm = s_begin; sgm < s_end; ++sgm) {
+        uint4 v[MS_VECS];
+        const uint4 *p = vsrc + sgm * (uint64_t)MS_SEG_VECS;
+#pragma unroll
+        for (int j = 0; j < MS_VECS; ++j) v[j] = __ldcs(p + j * EW_THREADS);
+        uint64_t bs = 0;
+        for (int k = 0; k + seg_shift < bm.nbits; ++k)
+            if ((sgm >> k) & 1ull) bs |= bm.contrib[k + seg_shift];
+        if (bs != cur) { flush(); cur = bs; }
+#pragma unroll
+        for (int j = 0; j < MS_VECS; ++j) {
+            double pr[2];
+            vec_probs<T>(v[j], pr);
+#pragma unroll
+            for (int u = 0; u < VE; ++u) acc[j][u] += pr[u];
+        }
+    }
+    flush();
+    if (!SMALL) return;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) hists[(size_t)blockIdx.x * nbins + b] = hist[b];
+    __threadfence();
+    __syncthreads();
+    unsigned *ticket = reinterpret_cast<unsigned *>(ws);
+    if (threadIdx.x == 0) last_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (last_flag) {
+        __threadfence();
+        for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
+            double a = 0.0;
+            for (unsigned g = 0; g < gridDim.x; ++g) a += __ldcg(&hists[(size_t)g * nbins + b]);
+            out[b] = a * inv;
+        }
+        if (threadIdx.x == 0) { *ticket = 0u; __threadfence(); }
+    }
+}
+
 // ---- collapse (state.py:368-378; density_operator.py:266-279) ------------------------------------
 template <typename C>
 __global__ void __launch_bounds__(EW_THREADS) collapse_kernel(C *__restrict__ dst, const C *src, int n,
@@ -255,16 +528,41 @@ __global__ void __launch_bounds__(EW_THREADS) diag_probs_kernel(double *__restri
 template <typename C>
 __global__ void __launch_bounds__(EW_THREADS) outer_kernel(C *__restrict__ rho, const C *__restrict__ psi, int n, double p,
                                                            const double *norm_psi, int accumulate) {
-    const double w = p * (norm_psi ? 1.0 / *norm_psi : 1.0);
-    const uint64_t N = 1ull << (2 * n);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        const C a = psi[compact_bits(i >> 1)];   // row index: odd bits
-        const C b = psi[compact_bits(i)];        // column index: even bits
-        double re = ((double)a.x * (double)b.x + (double)a.y * (double)b.y) * w;   // a * conj(b)
-        double im = ((double)a.y * (double)b.x - (double)a.x * (double)b.y) * w;
-        if (accumulate) { const C o = rho[i]; re += (double)o.x; im += (double)o.y; }
-        C r; r.x = (decltype(r.x))re; r.y = (decltype(r.y))im;
-        rho[i] = r;
+    // one 16-byte vector of rho per thread and step: for complex64 its two entries share the row amplitude
+    // and take the column amplitudes c, c | 1 (one 16-byte load of psi)
+    constexpr int VE = VecOf<C>::VE, LV = VecOf<C>::LV;
+    using R = decltype(C().x);
+    const R w = (R)(p * (norm_psi ? 1.0 / *norm_psi : 1.0));
+    const uint64_t NV = (1ull << (2 * n)) >> LV;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+#pragma unroll 2
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += stride) {
+        const uint64_t i = v << LV;
+        C a = psi[compact_bits(i >> 1)];   // row index: odd bits
+        a.x *= w; a.y *= w;
+        const uint64_t c = compact_bits(i);   // column index: even bits
+        C b[VE], r[VE];
+        if (VE == 2) {
+            const float4 bb = *reinterpret_cast<const float4 *>(psi + c);
+            b[0].x = bb.x; b[0].y = bb.y; b[VE - 1].x = bb.z; b[VE - 1].y = bb.w;
+        } else {
+            b[0] = psi[c];
+        }
+#pragma unroll
+        for (int u = 0; u < VE; ++u) {      // a * conj(b)
+            r[u].x = a.x * b[u].x + a.y * b[u].y;
+            r[u].y = a.y * b[u].x - a.x * b[u].y;
+        }
+        if (VE == 2) {
+            float4 *pr = reinterpret_cast<float4 *>(rho) + v;
+            float4 o;
+            o.x = (float)r[0].x; o.y = (float)r[0].y; o.z = (float)r[VE - 1].x; o.w = (float)r[VE - 1].y;
+            if (accumulate) { const float4 old = *pr; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            *pr = o;
+        } else {
+            if (accumulate) { const C old = rho[v]; r[0].x += old.x; r[0].y += old.y; }
+            rho[v] = r[0];
+        }
     }
 }
 
@@ -347,6 +645,11 @@ int misc_set_basis(void *buf, int n, int dtype, uint64_t index, cudaStream_t st)
 int misc_abs2(double *probs, const void *src, int n, int dtype, const double *norm_in, double *sum_out, void *ws,
               cudaStream_t st) {
     const uint64_t N = 1ull << n;
+    if (n >= 1) {
+        DISPATCH_C(dtype, (abs2_vec_kernel<C><<<ew_grid((N >> VecOf<C>::LV) / 4 + 1), EW_THREADS, 0, st>>>(
+                              probs, (const C *)src, N >> VecOf<C>::LV, norm_in, sum_out, ws)));
+        return check_launch();
+    }
     DISPATCH_C(dtype, (abs2_kernel<C><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>(probs, (const C *)src, N, norm_in,
                                                                                 sum_out, ws)));
     return check_launch();
@@ -371,6 +674,29 @@ int misc_lincomb(void *dst, const void *a, const void *b, int n, int dtype, cons
 int misc_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype, const double *norm_a,
               const double *norm_b, double *norm_out, void *ws, cudaStream_t st) {
     const uint64_t N = 1ull << (na + nb);
+    if (nb >= 12 && na <= 6) {
+        const uint64_t NVB = (1ull << nb) >> (dtype == QCS_C64 ? 1 : 0);
+        if (dtype == QCS_C64)
+            kron_small_a_kernel<float><<<ew_grid(NVB), EW_THREADS, 0, st>>>((float2 *)dst, (const float2 *)a, (const float2 *)b,
+                                                                           na, nb, norm_a, norm_b, norm_out, ws);
+        else if (dtype == QCS_C128)
+            kron_small_a_kernel<double><<<ew_grid(NVB), EW_THREADS, 0, st>>>((double2 *)dst, (const double2 *)a,
+                                                                            (const double2 *)b, na, nb, norm_a, norm_b,
+                                                                            norm_out, ws);
+        else return set_error(QCS_ERR_ARG, "bad dtype");
+        return check_launch();
+    }
+    if (nb >= 1) {
+        if (dtype == QCS_C64)
+            kron_vec_kernel<float><<<ew_grid(N / 8 + 1), EW_THREADS, 0, st>>>((float2 *)dst, (const float2 *)a, (const float2 *)b,
+                                                                             na, nb, norm_a, norm_b, norm_out, ws);
+        else if (dtype == QCS_C128)
+            kron_vec_kernel<double><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((double2 *)dst, (const double2 *)a,
+                                                                              (const double2 *)b, na, nb, norm_a, norm_b,
+                                                                              norm_out, ws);
+        else return set_error(QCS_ERR_ARG, "bad dtype");
+        return check_launch();
+    }
     DISPATCH_C(dtype, (kron_kernel<C><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((C *)dst, (const C *)a, (const C *)b, na,
                                                                                 nb, norm_a, norm_b, norm_out, ws)));
     return check_launch();
@@ -380,6 +706,18 @@ int misc_permute(void *dst, const void *src, int n, int dtype, const int32_t *sr
     BitList bl;
     if (int e = make_bitlist(bl, src_bit, n, n, false)) return e;
     const uint64_t N = 1ull << n;
+    if (dst == src) return set_error(QCS_ERR_ARG, "permute_bits cannot run in place");
+    if (n >= 15 && n <= 40) {
+        BinMap pm;
+        pm.nbits = n;
+        for (int b = 0; b < 40; ++b) pm.contrib[b] = b < n ? 1ull << src_bit[b] : 0ull;
+        const int lv = dtype == QCS_C64 ? 1 : 0;
+        uint64_t grid = (uint64_t)device_info().sms * 8;
+        const uint64_t nseg = N >> (11 + lv);
+        if (grid > nseg) grid = nseg;
+        DISPATCH_C(dtype, (permute_stream_kernel<C><<<(unsigned)grid, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, pm)));
+        return check_launch();
+    }
     DISPATCH_C(dtype, (permute_kernel<C><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((C *)dst, (const C *)src, n, bl)));
     return check_launch();
 }
@@ -389,13 +727,34 @@ static int marginal_impl(double *out, const T *src, int n, const BitList &bl, co
                          int64_t ws_bytes, cudaStream_t st) {
     const uint64_t N = 1ull << n;
     const int m = bl.m;
-    if (m <= MARG_SMALL_BITS) {
-        const size_t hist_bytes = sizeof(double) << m;
-        const int64_t avail = ws_bytes - WS_BYTES;
+    const int64_t avail = ws_bytes - WS_BYTES;
+    double *hists = reinterpret_cast<double *>(reinterpret_cast<char *>(ws) + WS_BYTES);
+    const bool small = m <= MARG_SMALL_BITS;
+    const size_t hist_bytes = small ? sizeof(double) << m : 0;
+    if (small && avail < (int64_t)hist_bytes) return set_error(QCS_ERR_ARG, "workspace too small for marginals");
+    const int seg_bits = 11 + VecOf<T>::LV;
+    if (n >= seg_bits + 3 && m < n && n <= 40) {
+        // streaming kernel: per-thread register accumulators, contiguous segment ranges per CTA
+        BinMap bm;
+        bm.nbits = n;
+        for (int b = 0; b < 40; ++b) bm.contrib[b] = 0;
+        for (int j = 0; j < m; ++j) bm.contrib[bl.pos[j]] = 1ull << (m - 1 - j);
+        const uint64_t nseg = N >> seg_bits;
+        uint64_t grid = (uint64_t)device_info().sms * 8;
+        if (grid > nseg) grid = nseg;
+        if (grid > MAX_GRID) grid = MAX_GRID;
+        if (small) {
+            if ((int64_t)grid * (int64_t)hist_bytes > avail) grid = (uint64_t)(avail / (int64_t)hist_bytes);
+            marginal_stream_kernel<T, true><<<(unsigned)grid, EW_THREADS, hist_bytes, st>>>(out, src, bm, m, norm_in, hists, ws);
+        } else {
+            if (cudaMemsetAsync(out, 0, sizeof(double) << m, st) != cudaSuccess) return set_error(QCS_ERR_CUDA, "memset failed");
+            marginal_stream_kernel<T, false><<<(unsigned)grid, EW_THREADS, 0, st>>>(out, src, bm, m, norm_in, nullptr, ws);
+        }
+        return check_launch();
+    }
+    if (small) {
         unsigned grid = ew_grid(N / MARG_SEG + 1, 4);
-        if (avail < (int64_t)hist_bytes) return set_error(QCS_ERR_ARG, "workspace too small for marginals");
         if ((int64_t)grid * (int64_t)hist_bytes > avail) grid = (unsigned)(avail / (int64_t)hist_bytes);
-        double *hists = reinterpret_cast<double *>(reinterpret_cast<char *>(ws) + WS_BYTES);
         marginal_small_kernel<T><<<grid, EW_THREADS, hist_bytes, st>>>(out, src, N, bl, norm_in, hists, ws);
     } else {
         const int exact = (m == n);
@@ -446,7 +805,7 @@ int misc_outer(void *rho, const void *psi, int n, int dtype, double p, const dou
                cudaStream_t st) {
     if (n < 1 || n > 31) return set_error(QCS_ERR_ARG, "bad qubit count");
     const uint64_t N = 1ull << (2 * n);
-    DISPATCH_C(dtype, (outer_kernel<C><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((C *)rho, (const C *)psi, n, p, norm_psi,
+    DISPATCH_C(dtype, (outer_kernel<C><<<ew_grid(N / 8 + 1), EW_THREADS, 0, st>>>((C *)rho, (const C *)psi, n, p, norm_psi,
                                                                                  accumulate)));
     return check_launch();
 }

@@ -1,0 +1,89 @@
+"""The large-state code paths of the streaming kernels (segment-decomposed marginals and bit permutation,
+vectorised tensor product and probabilities) against NumPy on states big enough to reach them."""
+import numpy as np
+import pytest
+
+import qcircuits_b200 as qc
+from oracle import qc_oracle as orc
+from qcircuits_b200 import _lib
+from tests.util import TOL, rand_state_vec, rel_err
+
+pytestmark = pytest.mark.gpu
+DTYPES = [np.complex128, np.complex64]
+
+
+def _state(vec, dtype):
+    return qc.State.from_column_vector(np.asarray(vec), dtype=dtype)
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_marginals_of_large_states_every_bit_class(dtype):
+    """Measured bits inside the per-thread part (0..8), the per-step part (9..11) and the segment part (>= 12),
+    few and many outcomes (shared-memory histogram up to 2^10, global atomics above)."""
+    rng = np.random.default_rng(5)
+    tol = TOL[np.dtype(dtype)]
+    for n in (15, 18, 20):
+        vec = rand_state_vec(rng, n)
+        s = _state(vec, dtype)
+        t = np.abs(vec.reshape([2] * n)) ** 2
+        cases = [[n - 1], [0], [n - 10], [n - 12], [n - 13], [0, n - 1], [n - 9, n - 11, n - 13, 0],
+                 list(range(n - 1, n - 11, -1)), list(range(0, 10)), [int(q) for q in rng.permutation(n)[:7]],
+                 [int(q) for q in rng.permutation(n)[:12]], [int(q) for q in rng.permutation(n)[:n - 1]]]
+        for qi in cases:
+            ps = s._measurement_probabilities(qi)
+            rest = tuple(a for a in range(n) if a not in qi)
+            want = np.transpose(t.sum(axis=rest) if rest else t, np.argsort(np.argsort(qi))).reshape(-1)
+            assert np.max(np.abs(ps - want)) < tol, (n, qi)
+            assert abs(ps.sum() - 1) < 10 * tol
+
+
+def test_marginals_of_a_real_probability_vector():
+    """QCS_F64 input (DensityOperator marginals run on the diagonal probabilities)."""
+    import torch
+    from qcircuits_b200._device import DeviceVector
+    rng = np.random.default_rng(6)
+    n = 16
+    p = rng.uniform(size=2 ** n)
+    p /= p.sum()
+    dev = torch.from_numpy(p).cuda()
+    dv = DeviceVector(_lib.alloc_amplitudes(1, np.complex128), None, 1, np.complex128)
+    for bits in ([n - 1, 0, 7], [3], list(range(4, 15)), [15, 14, 13, 12, 11]):
+        got = dv.marginals(bits, real_input=dev)
+        t = p.reshape([2] * n)
+        axes = [n - 1 - b for b in bits]
+        rest = tuple(a for a in range(n) if a not in axes)
+        want = np.transpose(t.sum(axis=rest), np.argsort(np.argsort(axes))).reshape(-1)
+        assert np.max(np.abs(got - want)) < 1e-13, bits
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_permute_qubits_of_large_states(dtype):
+    rng = np.random.default_rng(7)
+    tol = TOL[np.dtype(dtype)]
+    for n in (15, 17, 19):
+        vec = rand_state_vec(rng, n)
+        perms = [[int(a) for a in rng.permutation(n)] for _ in range(3)]
+        keep_last = [int(a) for a in rng.permutation(n - 1)] + [n - 1]       # flat bit 0 stays in place
+        swap_ends = list(range(n))
+        swap_ends[0], swap_ends[n - 1] = n - 1, 0
+        for axes in perms + [keep_last, swap_ends, list(range(n))]:
+            s = _state(vec, dtype)
+            s.permute_qubits(axes)
+            assert rel_err(s._t, np.transpose(vec.reshape([2] * n), axes)) < tol, (n, axes)
+            s.permute_qubits(axes, inverse=True)
+            assert rel_err(s.to_column_vector(), vec) < tol
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_tensor_product_and_probabilities_of_large_states(dtype):
+    rng = np.random.default_rng(8)
+    tol = TOL[np.dtype(dtype)]
+    for na, nb in ((9, 8), (16, 1), (1, 16), (12, 5)):
+        a, b = rand_state_vec(rng, na), rand_state_vec(rng, nb)
+        got = _state(a, dtype) * _state(b, dtype)
+        want = np.kron(a, b)
+        assert rel_err(got.to_column_vector(), want) < tol
+        probs = got.probabilities
+        assert probs.shape == (2,) * (na + nb)
+        assert np.max(np.abs(probs.reshape(-1) - np.abs(want) ** 2)) < tol
+        assert abs(got.dot(got) - 1) < 10 * tol
