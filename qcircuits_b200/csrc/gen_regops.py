@@ -83,6 +83,28 @@ class Gen:
         e('fma.rn.%s %s, c7, %s, %s;' % (ty, p[3], a1x, p[3])); e('fma.rn.%s %s, n7, %s, %s;' % (ty, p[2], a1y, p[2]))
         e('fma.rn.%s %s, c6, %s, %s;' % (ty, a1x, a1x, p[2])); e('fma.rn.%s %s, c6, %s, %s;' % (ty, a1y, a1y, p[3]))
 
+    # ---- packed FP32 (complex64 only): the real and imaginary part of one amplitude share a 64-bit register
+    # pair, so arms that apply the same real coefficients to both halves issue half the FP instructions
+    # (FADD2 / FMUL2 / FFMA2).  The pack / unpack moves vanish: the amplitudes already live in aligned pairs
+    # (they arrive through 64-bit shared-memory loads).
+    def packed(self):
+        return self.ty == 'f32'
+
+    def pk(self, x):
+        """packed register name of amplitude x (declared per arm by pack())"""
+        return 'P%d' % x
+
+    def pack(self, xs):
+        for x in xs:
+            self.emit('mov.b64 %s, {%s, %s};' % (self.pk(x), self.re(x), self.im(x)))
+
+    def unpack(self, xs):
+        for x in xs:
+            self.emit('mov.b64 {%s, %s}, %s;' % (self.re(x), self.im(x), self.pk(x)))
+
+    def bcast(self, dst, src):
+        self.emit('mov.b64 %s, {%s, %s};' % (dst, src, src))
+
     # ---- coefficient loads ----
     def ld4(self, regs=('c0', 'c1', 'c2', 'c3'), off=0):
         if self.ty == 'f32':
@@ -140,6 +162,7 @@ class Gen:
 
     def build(self):
         self.temps = set()
+        self.temps64 = set()
         rb, nx, ty = self.rb, self.nx, self.ty
         body_start = len(self.lines)
         J = range(4)
@@ -152,8 +175,15 @@ class Gen:
         for j in J:
             if j >= rb: absent('HAD'); continue
             self.arm('A_HAD%d' % j)
-            for x0, x1 in self.pairs(j):
-                self.addsub(self.re(x0), self.re(x1)); self.addsub(self.im(x0), self.im(x1))
+            if self.packed():
+                self.pack(range(nx))
+                for x0, x1 in self.pairs(j):
+                    self.emit('add.rn.f32x2 %s, %s, %s;' % (self.pk(x0), self.pk(x0), self.pk(x1)))
+                    self.emit('fma.rn.f32x2 %s, %s, QM2, %s;' % (self.pk(x1), self.pk(x1), self.pk(x0)))
+                self.unpack(range(nx))
+            else:
+                for x0, x1 in self.pairs(j):
+                    self.addsub(self.re(x0), self.re(x1)); self.addsub(self.im(x0), self.im(x1))
             self.done_arm()
         # REAL (plain, then predicated entry)
         def real_family(pred):
@@ -165,9 +195,22 @@ class Gen:
                     self.emit('bra.uni B_REAL%d;' % j)
                 else:
                     self.label('B_REAL%d' % j)
-                    for x0, x1 in self.pairs(j):
-                        self.map2(self.re(x0), self.re(x1), 'c0', 'c1', 'c2', 'c3')
-                        self.map2(self.im(x0), self.im(x1), 'c0', 'c1', 'c2', 'c3')
+                    if self.packed():
+                        for k in range(4):
+                            self.bcast('Q%d' % k, 'c%d' % k)
+                        self.pack(range(nx))
+                        for x0, x1 in self.pairs(j):
+                            t = self.tmp()
+                            self.temps64.add('pm1_%d' % t); self.temps64.add('pm2_%d' % t)
+                            self.emit('mul.rn.f32x2 pm1_%d, Q1, %s;' % (t, self.pk(x1)))
+                            self.emit('mul.rn.f32x2 pm2_%d, Q2, %s;' % (t, self.pk(x0)))
+                            self.emit('fma.rn.f32x2 %s, Q0, %s, pm1_%d;' % (self.pk(x0), self.pk(x0), t))
+                            self.emit('fma.rn.f32x2 %s, Q3, %s, pm2_%d;' % (self.pk(x1), self.pk(x1), t))
+                        self.unpack(range(nx))
+                    else:
+                        for x0, x1 in self.pairs(j):
+                            self.map2(self.re(x0), self.re(x1), 'c0', 'c1', 'c2', 'c3')
+                            self.map2(self.im(x0), self.im(x1), 'c0', 'c1', 'c2', 'c3')
                     self.done_arm()
         real_family(False)
         real_family(True)
@@ -175,8 +218,18 @@ class Gen:
         for j in J:
             if j >= rb: absent('REALU'); continue
             self.arm('A_REALU%d' % j)
-            for x0, x1 in self.pairs(j):
-                self.map2u(self.re(x0), self.re(x1), 'c0', 'c1', 'c2'); self.map2u(self.im(x0), self.im(x1), 'c0', 'c1', 'c2')
+            if self.packed():
+                for k in range(3):
+                    self.bcast('Q%d' % k, 'c%d' % k)
+                self.pack(range(nx))
+                for x0, x1 in self.pairs(j):
+                    self.emit('fma.rn.f32x2 %s, Q0, %s, %s;' % (self.pk(x0), self.pk(x1), self.pk(x0)))
+                    self.emit('mul.rn.f32x2 %s, %s, Q2;' % (self.pk(x1), self.pk(x1)))
+                    self.emit('fma.rn.f32x2 %s, Q1, %s, %s;' % (self.pk(x1), self.pk(x0), self.pk(x1)))
+                self.unpack(range(nx))
+            else:
+                for x0, x1 in self.pairs(j):
+                    self.map2u(self.re(x0), self.re(x1), 'c0', 'c1', 'c2'); self.map2u(self.im(x0), self.im(x1), 'c0', 'c1', 'c2')
             self.done_arm()
         # IMAG
         def imag_family(pred):
@@ -278,8 +331,15 @@ class Gen:
                     self.emit('bra.uni B_%s%d;' % (tag, k))
                 else:
                     self.label('B_%s%d' % (tag, k))
-                    for x in range(nx):
-                        if (x & mask) == mask:
+                    sel = [x for x in range(nx) if (x & mask) == mask]
+                    if self.packed():
+                        self.bcast('Q0', 'c0')
+                        self.pack(sel)
+                        for x in sel:
+                            self.emit('mul.rn.f32x2 %s, %s, Q0;' % (self.pk(x), self.pk(x)))
+                        self.unpack(sel)
+                    else:
+                        for x in sel:
                             self.emit('mul.%s %s, %s, c0;' % (ty, self.re(x), self.re(x)))
                             self.emit('mul.%s %s, %s, c0;' % (ty, self.im(x), self.im(x)))
                     self.done_arm()
@@ -324,6 +384,12 @@ class Gen:
         temps = sorted(self.temps)
         for i in range(0, len(temps), 8):
             head.append('.reg .%s %s;' % (ty, ', '.join(temps[i:i + 8])))
+        if self.packed():
+            head.append('.reg .b64 Q0, Q1, Q2, Q3, QM2, %s;' % ', '.join(self.pk(x) for x in range(self.nx)))
+            t64 = sorted(self.temps64)
+            for i in range(0, len(t64), 8):
+                head.append('.reg .b64 %s;' % ', '.join(t64[i:i + 8]))
+            head.append('mov.b64 QM2, 0xC0000000C0000000;')
         targets = ', '.join(self.labels)
         # software pipeline: the record of op i+1 is fetched while op i runs; the first four coefficients of
         # op i are fetched in the head (every arm but HAD / CX / END uses them) so that their latency overlaps
