@@ -923,24 +923,65 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             --npend;
             continue;
         }
-        // choose the ops of this register sweep
+        // choose the ops of this register sweep.  select(fixed, ...) walks the pending ops in order: an op is taken
+        // if nothing it must follow is left behind and (one-target dense op) its target is a register bit; with
+        // fixed == 0 the register set grows greedily with the first distinct targets met.
         uint32_t S_local = 0;                  // tile-local mask of the register bits
         int S_count = 0;
-        uint64_t blk_nd = 0, blk_d = 0;
         int taken[QCS_MAX_OPS], ntaken = 0, rest[QCS_MAX_OPS], nrest = 0;
-        for (int i = 0; i < npend; ++i) {
-            const int idx = pending[i];
-            const HostOp &h = hop[idx];
-            bool can = h.kind != 2 && (h.nd_mask & (blk_nd | blk_d)) == 0 && (h.d_mask & blk_nd) == 0;
-            if (can && h.kind == 0) {
-                const uint32_t tbit = 1u << local_of(ops[idx].bitpos[0]);
-                if (!(S_local & tbit)) {
-                    if (S_count < nreg) { S_local |= tbit; ++S_count; }
-                    else can = false;
+        auto select = [&](uint32_t fixed, uint32_t &S_out, int &S_cnt, int *tk, int &ntk, int *rs, int &nrs) -> int {
+            uint64_t blk_nd = 0, blk_d = 0;
+            uint32_t S = fixed;
+            int cnt = __builtin_popcount(fixed), score = 0;
+            ntk = nrs = 0;
+            for (int i = 0; i < npend; ++i) {
+                const int idx = pending[i];
+                const HostOp &h = hop[idx];
+                bool can = h.kind != 2 && (h.nd_mask & (blk_nd | blk_d)) == 0 && (h.d_mask & blk_nd) == 0;
+                if (can && h.kind == 0) {
+                    const uint32_t tbit = 1u << local_of(ops[idx].bitpos[0]);
+                    if (!(S & tbit)) {
+                        if (!fixed && cnt < nreg) { S |= tbit; ++cnt; }
+                        else can = false;
+                    }
+                }
+                if (can) { tk[ntk++] = idx; score += h.kind == 0 ? 16 : 1; }
+                else { rs[nrs++] = idx; blk_nd |= h.nd_mask; blk_d |= h.d_mask; }
+            }
+            S_out = S; S_cnt = cnt;
+            return score;
+        };
+        int best_score = select(0u, S_local, S_count, taken, ntaken, rest, nrest);
+        if (nreg >= 2 && tune_int("QCS_SWEEP_SEARCH", 1)) {
+            // alternatives: register sets drawn from the first distinct dense targets still pending (always with
+            // the first one, so that the sweep makes progress); keep the set that absorbs the most ops
+            int cand[8], ncand = 0;
+            for (int i = 0; i < npend && ncand < 8; ++i) {
+                const HostOp &h = hop[pending[i]];
+                if (h.kind == 2) break;
+                if (h.kind != 0) continue;
+                const int lb = local_of(ops[pending[i]].bitpos[0]);
+                bool dup = false;
+                for (int c = 0; c < ncand; ++c) dup |= cand[c] == lb;
+                if (!dup) cand[ncand++] = lb;
+            }
+            if (ncand > nreg) {
+                int tk2[QCS_MAX_OPS], rs2[QCS_MAX_OPS];
+                for (uint32_t sub = 0; sub < (1u << (ncand - 1)); ++sub) {
+                    if (__builtin_popcount(sub) != nreg - 1) continue;
+                    uint32_t fixed = 1u << cand[0];
+                    for (int c = 1; c < ncand; ++c)
+                        if ((sub >> (c - 1)) & 1u) fixed |= 1u << cand[c];
+                    uint32_t S2;
+                    int c2, n2, r2;
+                    const int sc = select(fixed, S2, c2, tk2, n2, rs2, r2);
+                    if (sc > best_score) {
+                        best_score = sc; S_local = S2; S_count = c2; ntaken = n2; nrest = r2;
+                        for (int i = 0; i < n2; ++i) taken[i] = tk2[i];
+                        for (int i = 0; i < r2; ++i) rest[i] = rs2[i];
+                    }
                 }
             }
-            if (can) taken[ntaken++] = idx;
-            else { rest[nrest++] = idx; blk_nd |= h.nd_mask; blk_d |= h.d_mask; }
         }
         // complete the register set: first the aligned blocks that already hold a register bit, then from the top
         for (int blk = 0; blk * nreg < m && S_count < nreg; ++blk) {
