@@ -154,6 +154,12 @@ int qcs_diag_probs(double *probs, const void *rho, int n, int dtype, double *sum
 int qcs_outer_accumulate(void *rho, const void *psi, int n, int dtype, double p,
                          const double *norm_psi, int accumulate, qcs_stream stream);
 
+/* DensityOperator._reduced_tensor (density_operator.py:127-138: transposes + np.einsum('ii...->...')):
+ * out = partial trace of the d-qubit rho over every qubit not listed; output qubit j is qubit keep[j]
+ * (same interleaved row / column layout on 2 * nkeep bits).  out must not alias rho. */
+int qcs_partial_trace(void *out, const void *rho, int d, int dtype, const int32_t *keep, int nkeep,
+                      qcs_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ PROTOTYPES = {
     'qcs_collapse': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_uint64, c_int, c_double,
                              c_void_p, c_void_p, c_void_p]),
     'qcs_diag_probs': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'qcs_partial_trace': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     'qcs_outer_accumulate': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_int, c_void_p]),
 }
 

@@ -192,6 +192,12 @@ int qcs_diag_probs(double *probs, const void *rho, int n, int dtype, double *sum
     return misc_diag_probs(probs, rho, n, dtype, sum_out, ws, (cudaStream_t)stream);
 }
 
+int qcs_partial_trace(void *out, const void *rho, int d, int dtype, const int32_t *keep, int nkeep, qcs_stream stream) {
+    if (!out || !rho || !keep) return set_error(QCS_ERR_ARG, "null argument");
+    if (dtype != QCS_C64 && dtype != QCS_C128) return set_error(QCS_ERR_ARG, "dtype must be QCS_C64 or QCS_C128");
+    return misc_partial_trace(out, rho, d, dtype, keep, nkeep, (cudaStream_t)stream);
+}
+
 int qcs_outer_accumulate(void *rho, const void *psi, int n, int dtype, double p, const double *norm_psi,
                          int accumulate, qcs_stream stream) {
     if (!rho || !psi) return set_error(QCS_ERR_ARG, "null pointer");

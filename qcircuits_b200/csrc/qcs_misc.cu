@@ -566,6 +566,51 @@ __global__ void __launch_bounds__(EW_THREADS) outer_kernel(C *__restrict__ rho, 
     }
 }
 
+// ---- partial trace (density_operator.py:127-138, np.einsum('ii...->...')) ------------------------
+// out[o] = sum_t rho[base(o) | diag(t)]: base(o) scatters the 2k bits of the output index (row / column bits of
+// the kept qubits, in the caller's order) to their flat bits in rho, diag(t) sets the row AND the column bit
+// of traced qubit j to bit j of t.  Only 4^k 2^(d-k) of the 4^d entries are read.  One CTA per output entry
+// (strided over the grid): its threads split the 2^(d-k) terms, float64 accumulation, block reduction.
+struct TraceMap {
+    int32_t nout_bits, ntraced;
+    uint64_t out_contrib[64];     // flat bit of rho set by output-index bit b
+    uint64_t tr_contrib[32];      // the two flat bits of rho set by bit j of the traced configuration
+};
+template <typename C>
+__global__ void __launch_bounds__(EW_THREADS) partial_trace_kernel(C *__restrict__ out, const C *__restrict__ rho,
+                                                                  const __grid_constant__ TraceMap tm) {
+    __shared__ double red[2][EW_THREADS / 32];
+    const uint64_t nout = 1ull << tm.nout_bits, nterms = 1ull << tm.ntraced;
+    for (uint64_t o = blockIdx.x; o < nout; o += gridDim.x) {
+        uint64_t base = 0;
+        for (int b = 0; b < tm.nout_bits; ++b)
+            if ((o >> b) & 1ull) base |= tm.out_contrib[b];
+        double re = 0.0, im = 0.0;
+        for (uint64_t t = threadIdx.x; t < nterms; t += blockDim.x) {
+            uint64_t idx = base;
+            for (int j = 0; j < tm.ntraced; ++j)
+                if ((t >> j) & 1ull) idx |= tm.tr_contrib[j];
+            const C v = rho[idx];
+            re += (double)v.x; im += (double)v.y;
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            re += __shfl_down_sync(0xffffffffu, re, sh);
+            im += __shfl_down_sync(0xffffffffu, im, sh);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { red[0][warp] = re; red[1][warp] = im; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sr = 0.0, si = 0.0;
+            for (int w = 0; w < EW_THREADS / 32; ++w) { sr += red[0][w]; si += red[1][w]; }
+            C r; r.x = (decltype(r.x))sr; r.y = (decltype(r.y))si;
+            out[o] = r;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- dense fallback: operator on k > 4 qubits (operators.py:261 with a wide operator) ------------
 constexpr int DT = 16;
 template <typename R>
@@ -807,6 +852,32 @@ int misc_outer(void *rho, const void *psi, int n, int dtype, double p, const dou
     const uint64_t N = 1ull << (2 * n);
     DISPATCH_C(dtype, (outer_kernel<C><<<ew_grid(N / 8 + 1), EW_THREADS, 0, st>>>((C *)rho, (const C *)psi, n, p, norm_psi,
                                                                                  accumulate)));
+    return check_launch();
+}
+
+int misc_partial_trace(void *out, const void *rho, int d, int dtype, const int32_t *keep, int nkeep, cudaStream_t st) {
+    if (d < 1 || d > 20) return set_error(QCS_ERR_ARG, "bad qubit count");
+    if (nkeep < 1 || nkeep > d) return set_error(QCS_ERR_ARG, "must keep between 1 and d qubits");
+    if (out == rho) return set_error(QCS_ERR_ARG, "partial trace cannot run in place");
+    TraceMap tm;
+    tm.nout_bits = 2 * nkeep;
+    tm.ntraced = d - nkeep;
+    uint32_t kept = 0;
+    for (int j = 0; j < nkeep; ++j) {
+        if (keep[j] < 0 || keep[j] >= d) return set_error(QCS_ERR_ARG, "qubit index out of range");
+        if (kept & (1u << keep[j])) return set_error(QCS_ERR_ARG, "repeated qubit index");
+        kept |= 1u << keep[j];
+        // output qubit j (0 = most significant pair of the output index) <- qubit keep[j] of rho
+        const int ob = 2 * (nkeep - 1 - j), ib = 2 * (d - 1 - keep[j]);
+        tm.out_contrib[ob] = 1ull << ib;              // column bit
+        tm.out_contrib[ob + 1] = 1ull << (ib + 1);    // row bit
+    }
+    int t = 0;
+    for (int q = 0; q < d; ++q)
+        if (!((kept >> q) & 1u)) tm.tr_contrib[t++] = 3ull << (2 * (d - 1 - q));
+    const uint64_t nout = 1ull << tm.nout_bits;
+    uint64_t grid = nout < (uint64_t)MAX_GRID ? nout : (uint64_t)MAX_GRID;
+    DISPATCH_C(dtype, (partial_trace_kernel<C><<<(unsigned)grid, EW_THREADS, 0, st>>>((C *)out, (const C *)rho, tm)));
     return check_launch();
 }
 

@@ -149,17 +149,20 @@ class DensityOperator(OperatorBase):
                                                 track_norm=False))
 
     # -- partial trace / purification (host: SURVEY 8f-4, LAPACK-class work outside the hot path) ---------------
-    def _reduced_tensor(self, retain_indices):
-        """Trace out every qubit not listed (density_operator.py:127-138), on the exported tensor."""
+    def _reduced_device(self, retain_indices):
+        """Trace out every qubit not listed (density_operator.py:127-138) on the device: qcs_partial_trace
+        replaces the two transposes and the np.einsum('ii...->...') of the reference."""
         d = self.rank // 2
+        retain = [int(q) for q in retain_indices]
+        out = DeviceVector(_lib.alloc_amplitudes(2 * len(retain), self._dv.dtype), None, 2 * len(retain), self._dv.dtype)
+        _lib.check(_lib.load().qcs_partial_trace(out.buf.data_ptr(), self._dv.buf.data_ptr(), d, self._dv.code,
+                                                 _lib.int32_array(retain), len(retain), _lib.stream_ptr()))
+        return out
+
+    def _reduced_tensor(self, retain_indices):
+        """The reduced tensor as a host array (the reference's private helper, density_operator.py:127-138)."""
         retain = list(retain_indices)
-        traced = list(set(range(d)) - set(retain))
-        order = traced + retain
-        t = np.transpose(self._t, [a for q in order for a in (2 * q, 2 * q + 1)])
-        n_tr = len(traced)
-        rows_cols_first = list(range(0, 2 * n_tr, 2)) + list(range(1, 2 * n_tr, 2)) + list(range(2 * n_tr, 2 * d))
-        t = np.transpose(t, rows_cols_first).reshape([2 ** n_tr, 2 ** n_tr] + [2] * (2 * len(retain)))
-        return np.einsum('ii...->...', t)
+        return self._reduced_device(retain).to_host().reshape([2] * (2 * len(retain)))
 
     def reduced_density_operator(self, qubit_indices):
         """Reduced density operator of the listed qubits (density_operator.py:169-200)."""
@@ -173,7 +176,7 @@ class DensityOperator(OperatorBase):
                              'where d is the rank of the state vector.')
         if len(qubit_indices) != len(set(qubit_indices)):
             raise ValueError('Qubit indices list contains repeated elements.')
-        return DensityOperator(self._reduced_tensor(qubit_indices), dtype=self._dv.dtype)
+        return DensityOperator(self._reduced_device(qubit_indices))
 
     def purify(self):
         """A 2d-qubit pure state whose reduced density operator on the first d qubits is this one

@@ -87,3 +87,31 @@ def test_tensor_product_and_probabilities_of_large_states(dtype):
         assert probs.shape == (2,) * (na + nb)
         assert np.max(np.abs(probs.reshape(-1) - np.abs(want) ** 2)) < tol
         assert abs(got.dot(got) - 1) < 10 * tol
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_partial_trace_against_the_oracle(dtype):
+    """DensityOperator.reduced_density_operator on the device (qcs_partial_trace) vs the oracle's restatement
+    of density_operator.py:127-138, for mixed states, any retain order, few and many traced qubits."""
+    rng = np.random.default_rng(9)
+    tol = TOL[np.dtype(dtype)] * 4
+    for d in (2, 4, 7):
+        states = [rand_state_vec(rng, d).reshape([2] * d) for _ in range(3)]
+        ps = rng.uniform(size=3)
+        ps /= ps.sum()
+        rho_t = orc.from_ensemble(states, ps)
+        rho = qc.DensityOperator(rho_t, dtype=dtype)
+        cases = [[0], [d - 1], list(range(d)), list(range(d - 1, -1, -1))]
+        if d >= 4:
+            cases += [[2, 0], [1, 3, 2], [int(q) for q in rng.permutation(d)[:d - 1]]]
+        for retain in cases:
+            got = rho.reduced_density_operator(retain)
+            want = orc.reduced_tensor(rho_t, retain)
+            assert got.rank == 2 * len(retain)
+            assert rel_err(got._t.reshape(-1), np.asarray(want).reshape(-1)) < tol, (d, retain)
+            assert abs(got.probabilities.sum() - 1) < 1e-4
+    # a pure state through State.reduced_density_operator (state.py:285-305)
+    psi = rand_state_vec(rng, 9)
+    got = qc.State.from_column_vector(psi, dtype=dtype).reduced_density_operator([8, 3])
+    want = orc.reduced_tensor(orc.outer_product(psi.reshape([2] * 9)), [8, 3])
+    assert rel_err(got._t.reshape(-1), np.asarray(want).reshape(-1)) < tol
