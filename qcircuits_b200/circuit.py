@@ -51,12 +51,13 @@ def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None, 
     an earlier one only if they commute (they share no bit on which either acts non-diagonally).  A tile is
     the low L flat bits plus a window of H consecutive higher bits with L + H = tile_bits; L ranges from the
     engine's preferred contiguous run down to ``low_shrink`` bits less (a shorter contiguous run buys a wider
-    window: for nearest-neighbour circuits the gates a window absorbs grow with the square of its width).
+    window: for nearest-neighbour circuits the gates a window absorbs grow with the square of its width; fused
+    passes are compute-bound, so 128-byte contiguous runs cost nothing measurable -- QCS_LOW_SHRINK, default 6).
     ``gates`` are records with nd_mask / d_mask / entries / wide over the n flat bits of the (local) state.
     Returns lists of indices into ``gates``."""
     low, tile = tile_limits(dtype)
     if low_shrink is None:
-        low_shrink = int(os.environ.get('QCS_LOW_SHRINK', '3'))
+        low_shrink = int(os.environ.get('QCS_LOW_SHRINK', '6'))
     geoms = []
     if high_bits is not None:
         geoms.append((min(low, n), max(0, min(high_bits, n - min(low, n)))))

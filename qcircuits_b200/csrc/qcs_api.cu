@@ -39,6 +39,14 @@ int tune_int(const char *name, int fallback) {
     return std::atoi(e);
 }
 
+// Largest tile in bits.  By default 32 KB tiles (two 256-thread CTAs per SM): measured faster than 64 KB tiles
+// (one 512-thread CTA per SM, every sweep in lockstep across the SM) even though a 64 KB tile holds one more
+// window bit -- 300 vs 326 ms on the headline circuit.  QCS_TILE_SHRINK=0 allows the 64 KB tiles.
+int tile_max_bits(int dtype) {
+    const int full = dtype == QCS_C64 ? TILE_MAX_BITS_C64 : TILE_MAX_BITS_C128;
+    return full - (tune_int("QCS_TILE_SHRINK", 1) ? 1 : 0);
+}
+
 static int g_tile_mode = -1;
 int tile_mode() {
     if (g_tile_mode < 0) {
@@ -76,7 +84,7 @@ int qcs_set_tile_mode(int mode) {
 int qcs_tile_limits(int dtype, int *low_bits, int *tile_bits) {
     if (dtype != QCS_C64 && dtype != QCS_C128) return set_error(QCS_ERR_ARG, "bad dtype");
     if (low_bits) *low_bits = dtype == QCS_C64 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
-    if (tile_bits) *tile_bits = dtype == QCS_C64 ? TILE_MAX_BITS_C64 : TILE_MAX_BITS_C128;
+    if (tile_bits) *tile_bits = tile_max_bits(dtype);
     return QCS_OK;
 }
 

@@ -83,6 +83,7 @@ static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes"
 struct DeviceInfo { int sms; size_t smem_per_sm; };
 const DeviceInfo &device_info();
 int tile_mode();
+int tile_max_bits(int dtype);
 int tune_int(const char *name, int fallback);
 int set_error(int code, const char *msg);
 

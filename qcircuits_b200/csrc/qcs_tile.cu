@@ -818,7 +818,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
 
     // ---- tile geometry: low L bits + the dense targets above them, padded to the minimum tile -------
     const int lpref = c64 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
-    const int mmax = c64 ? TILE_MAX_BITS_C64 : TILE_MAX_BITS_C128;
+    const int mmax = tile_max_bits(dtype);
     const int mmin = c64 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
     int L = n < lpref ? n : lpref;
     int H = 0;

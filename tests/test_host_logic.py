@@ -151,9 +151,9 @@ def test_libqcs_exports_every_declared_symbol():
     assert bound.qcs_workspace_bytes() > 0
     low, tile = ctypes.c_int(), ctypes.c_int()
     assert bound.qcs_tile_limits(_lib.QCS_C64, ctypes.byref(low), ctypes.byref(tile)) == 0
-    assert (low.value, tile.value) == (10, 13)
+    assert (low.value, tile.value) == (10, 12)          # 8 KB preferred contiguous run, 32 KB tiles
     assert bound.qcs_tile_limits(_lib.QCS_C128, ctypes.byref(low), ctypes.byref(tile)) == 0
-    assert (low.value, tile.value) == (9, 12)
+    assert (low.value, tile.value) == (9, 11)
     assert bound.qcs_tile_limits(7, None, None) < 0 and b'dtype' in bound.qcs_last_error()
 
 

@@ -41,9 +41,9 @@ def test_controls_outside_the_tile_become_predicates():
 
 
 def test_tile_shrinks_its_contiguous_run_for_many_high_targets():
-    # five dense targets above bit 10: the planner gives up two contiguous low bits (L = 8, H = 5)
+    # five dense targets above bit 10: the planner gives up contiguous low bits (L = 7, H = 5 in a 32 KB tile)
     st = _stats(26, np.complex64, [(H, [b]) for b in (12, 14, 16, 18, 20)])
-    assert st[0] == 13
+    assert st[0] == 12
     lib = _lib.load()
     ops, keep = make_ops([(_gates.analyze(H), [b], False) for b in range(10, 26)])
     out = (ctypes.c_int32 * 128)()
