@@ -88,7 +88,7 @@ def main():
     ap.add_argument('--qubits', type=int, default=None)
     ap.add_argument('--depth', type=int, default=40)
     ap.add_argument('--dtype', default='c64', choices=['c64', 'c128'])
-    ap.add_argument('--max-ops', type=int, default=64)
+    ap.add_argument('--max-ops', type=int, default=128)
     ap.add_argument('--no-fuse', action='store_true')
     ap.add_argument('--cpu-qubits', type=int, default=24)
     ap.add_argument('--cpu-budget', type=float, default=12.0)

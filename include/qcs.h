@@ -44,7 +44,7 @@ extern "C" {
 #define QCS_F64 2  /* real float64 input (marginals of a probability vector) */
 
 #define QCS_MAX_OP_QUBITS 4 /* largest gate the tile engine applies in one op   */
-#define QCS_MAX_OPS 64      /* ops per fused pass                                */
+#define QCS_MAX_OPS 128     /* ops per fused pass                                */
 
 #define QCS_OP_DENSE 0
 #define QCS_OP_DIAG 1

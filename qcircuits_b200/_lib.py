@@ -12,7 +12,7 @@ import numpy as np
 QCS_C64, QCS_C128, QCS_F64 = 0, 1, 2
 QCS_OP_DENSE, QCS_OP_DIAG = 0, 1
 QCS_MAX_OP_QUBITS = 4
-QCS_MAX_OPS = 64
+QCS_MAX_OPS = 128
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libqcs.so')

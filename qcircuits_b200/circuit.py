@@ -46,7 +46,7 @@ def tile_limits(dtype):
     return low.value, tile.value
 
 
-def schedule_passes(gates, n, dtype, max_ops=24, lookahead=512, high_bits=None, low_shrink=None):
+def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None, low_shrink=None):
     """Greedy fusion: repeatedly pick the tile that admits the most pending gates, where a gate may overtake
     an earlier one only if they commute (they share no bit on which either acts non-diagonally).  A tile is
     the low L flat bits plus a window of H consecutive higher bits with L + H = tile_bits; L ranges from the
@@ -236,7 +236,7 @@ class Circuit:
         return len(self.gates)
 
     # -- scheduling ------------------------------------------------------------------------------------
-    def schedule(self, dtype=np.complex128, fuse=True, max_ops=24, lookahead=512):
+    def schedule(self, dtype=np.complex128, fuse=True, max_ops=128, lookahead=512):
         """Group the gates into passes.  Returns a list of lists of gate indices (execution order
         inside a pass = list order).  ``fuse=False`` gives one pass per gate."""
         if not fuse:
@@ -262,7 +262,7 @@ class Circuit:
         return comp
 
     # -- execution ---------------------------------------------------------------------------------------
-    def run(self, state, fuse=True, max_ops=24):
+    def run(self, state, fuse=True, max_ops=128):
         """Apply the circuit to ``state`` and return the new State; the argument is left untouched
         (the first pass writes a fresh buffer, later passes update it in place)."""
         if state.rank != self.n:
@@ -296,7 +296,7 @@ class Circuit:
             which ^= 1
         return State(cur)
 
-    def run_host(self, host_in, host_out, fuse=True, max_ops=24):
+    def run_host(self, host_in, host_out, fuse=True, max_ops=128):
         """Host-buffer entry: ``host_in`` / ``host_out`` are (pinned) torch CPU tensors holding 2^n
         complex amplitudes (complex64/complex128 or interleaved reals).  Copies the state to the
         device, runs the circuit, copies the normalised result back.  Returns ``host_out``."""
@@ -312,6 +312,6 @@ class Circuit:
         t.cuda.current_stream().synchronize()
         return host_out
 
-    def stats(self, dtype=np.complex128, fuse=True, max_ops=24):
+    def stats(self, dtype=np.complex128, fuse=True, max_ops=128):
         """(number of passes, number of gates) for the schedule used by run()."""
         return len(self._compiled(dtype, fuse, max_ops)), len(self.gates)

@@ -77,7 +77,7 @@ struct TileProgram {
     alignas(16) unsigned char mats[MATBYTES];
 };
 using SmallProg = TileProgram<4, 34, 2, 4096 + 64>;
-using LargeProg = TileProgram<72, 260, QCS_MAX_OPS, 12288>;
+using LargeProg = TileProgram<72, 420, 64, 12288>;
 static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes");
 
 struct DeviceInfo { int sms; size_t smem_per_sm; };

@@ -261,7 +261,7 @@ class ShardedState:
         self.norm = None
         return self
 
-    def run(self, circuit, max_ops=24):
+    def run(self, circuit, max_ops=128):
         """Apply a Circuit (its gates are on logical qubits).  Collective: every rank calls it."""
         gates = [_LogicalGate(gt.plan, [circuit.n - 1 - b for b in gt.bits]) for gt in circuit.gates]
         steps, phys = dist_schedule(gates, self.n, self.g, self.phys)
