@@ -15,13 +15,15 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 600 python bench.py --steps 2 --warmup 1 --skip-cpu --skip-e2e > gpurun_out/bench_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 1 --skip-cpu --skip-e2e > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?" | tee -a gpurun_out/summary.txt
-export NCU_MAX_OPS=64
+export NCU_MAX_OPS=128
 timeout 300 python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none -k regex:tile_kernel -c 18 -o /tmp/prof python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu exit $?" | tee -a gpurun_out/summary.txt
 ncu -i /tmp/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile_kernel -s 10 -c 1 -o /tmp/prof_fused python tools/ncu_target.py > gpurun_out/ncu_fused.log 2>&1
 ncu -i /tmp/prof_fused.ncu-rep --page source --csv > gpurun_out/prof_source_fused.csv 2>/dev/null
+timeout 300 python tools/pass_times.py > gpurun_out/pass_times.log 2>&1
+timeout 300 python tools/microbench_misc.py > gpurun_out/microbench_misc.log 2>&1
 cat gpurun_out/summary.txt
 tail -n 4 gpurun_out/pytest_gpu.log
 python - <<'PY'

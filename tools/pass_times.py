@@ -16,7 +16,7 @@ def main():
     from qcircuits_b200 import _lib
     from qcircuits_b200.workloads import layered_circuit
     n = int(os.environ.get('PT_N', '30'))
-    max_ops = int(os.environ.get('PT_MAX_OPS', '48'))
+    max_ops = int(os.environ.get('PT_MAX_OPS', '128'))
     dtype = np.complex64 if os.environ.get('PT_DTYPE', 'c64') == 'c64' else np.complex128
     lib = _lib.load()
     circ = layered_circuit(n, 40, seed=1234)
