@@ -44,7 +44,10 @@ int tune_int(const char *name, int fallback) {
 // window bit -- 300 vs 326 ms on the headline circuit.  QCS_TILE_SHRINK=0 allows the 64 KB tiles.
 int tile_max_bits(int dtype) {
     const int full = dtype == QCS_C64 ? TILE_MAX_BITS_C64 : TILE_MAX_BITS_C128;
-    return full - (tune_int("QCS_TILE_SHRINK", 1) ? 1 : 0);
+    int shrink = tune_int("QCS_TILE_SHRINK", 1);       // 2: 16 KB tiles, four 128-thread CTAs per SM
+    if (shrink < 0) shrink = 0;
+    if (shrink > 2) shrink = 2;
+    return full - shrink;
 }
 
 static int g_tile_mode = -1;

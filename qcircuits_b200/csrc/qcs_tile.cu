@@ -437,7 +437,7 @@ __device__ __forceinline__ void vec_norm_acc(double &acc, const uint4 v, double)
 // still holds 16 warps
 template <typename R, int MT> struct PipeThreads {
     static constexpr int MSTD = sizeof(typename CxT<R>::T) == 8 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
-    static constexpr int value = MT == MSTD + 1 ? 2 * TILE_THREADS : TILE_THREADS;
+    static constexpr int value = MT == MSTD + 1 ? 2 * TILE_THREADS : (MT == MSTD - 1 ? TILE_THREADS / 2 : TILE_THREADS);
 };
 
 template <typename R, typename Prog, int MT, int OCC>
@@ -729,18 +729,19 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         int ctas = tune_int("QCS_PIPE_CTAS", 2);
         if (ctas < 1) ctas = 1;
         if (ctas > 2) ctas = 2;
-        const bool fast12 = fast_ok && m == MSTD, fast13 = fast_ok && m == MSTD + 1;
-        if (!(fast12 || fast13) && ctas > 2) ctas = 2;
+        const bool fast12 = fast_ok && m == MSTD, fast13 = fast_ok && m == MSTD + 1, fast11 = fast_ok && m == MSTD - 1;
         void (*kern)(const Prog) = tile_kernel_pipe<R, Prog, 0, 2>;
         if (fast12) kern = tile_kernel_pipe<R, Prog, MSTD, 2>;
         else if (fast13) { kern = tile_kernel_pipe<R, Prog, MSTD + 1, 1>; ctas = 1; }
-        const bool is_fast = fast12 || fast13;
+        else if (fast11) { kern = tile_kernel_pipe<R, Prog, MSTD - 1, 4>; ctas = tune_int("QCS_PIPE_CTAS11", 4) == 3 ? 3 : 4; }
+        const bool is_fast = fast12 || fast13 || fast11;
         static bool attr_done = false;
         if (!attr_done) {
             const int lim = (int)TILE_SMEM_BUDGET;
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+            cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD - 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             attr_done = true;
         }
         const size_t stage_bytes = PaddedLayout<C>::bytes(m);
@@ -749,7 +750,6 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         while (S < 2 && ctas > 1) {
             --ctas;
             S = (int)((sm_smem / ctas - prog - 1024) / stage_bytes);
-            if (fast12) kern = tile_kernel_pipe<R, Prog, MSTD, 2>;
         }
         S = S > TILE_MAX_STAGES ? TILE_MAX_STAGES : S;
         while (S > 2 && (size_t)S * stage_bytes + prog > TILE_SMEM_BUDGET) --S;
@@ -762,7 +762,7 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         uint64_t grid = (uint64_t)dev.sms * ctas;
         if (grid > P.ntiles) grid = P.ntiles;
         if (grid > MAX_GRID) grid = MAX_GRID;
-        int threads = fast13 ? 2 * TILE_THREADS : TILE_THREADS;
+        int threads = fast13 ? 2 * TILE_THREADS : (fast11 ? TILE_THREADS / 2 : TILE_THREADS);
         if (!is_fast)
             while (threads > 32 && (1u << m) < (unsigned)threads * 2u) threads >>= 1;
         kern<<<(unsigned)grid, threads, smem, stream>>>(P);
@@ -819,7 +819,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     // ---- tile geometry: low L bits + the dense targets above them, padded to the minimum tile -------
     const int lpref = c64 ? TILE_LOW_BITS_C64 : TILE_LOW_BITS_C128;
     const int mmax = tile_max_bits(dtype);
-    const int mmin = c64 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128;
+    const int mmin = (c64 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128) < mmax ? (c64 ? TILE_MIN_BITS_C64 : TILE_MIN_BITS_C128) : mmax;
     int L = n < lpref ? n : lpref;
     int H = 0;
     for (;; --L) {
