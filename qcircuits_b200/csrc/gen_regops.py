@@ -19,7 +19,8 @@ import sys
 
 
 class Gen:
-    def __init__(self, ty, rb):
+    def __init__(self, ty, rb, with_gen2=True):
+        self.with_gen2 = with_gen2        # False: the lean interpreter (GEN2 ids jump to the loop head)
         self.ty = ty                      # 'f32' | 'f64'
         self.rb = rb
         self.nx = 1 << rb
@@ -369,6 +370,102 @@ class Gen:
         # END of the sweep's op list
         self.arm('A_END')
         self.emit('bra.uni L_DONE;')
+        # GEN2: any complex 4x4 on two register bits (pair p = (j1 < j2), matrix index = bit j2 : bit j1), in place:
+        # the off-diagonal terms of all four outputs go to temporaries first, then each amplitude is updated by
+        # its own diagonal entry (so no copy back).  32 coefficients e0..e31 (row-major, re / im).
+        def gen2_groups(j1, j2):
+            out = []
+            for x0 in range(nx):
+                if (x0 >> j1) & 1 or (x0 >> j2) & 1:
+                    continue
+                out.append([x0 | ((i & 1) << j1) | (((i >> 1) & 1) << j2) for i in range(4)])
+            return out
+
+        def gen2_row(y, xs, T, coef):
+            """T[y] = sum_{x != y} M[y][x] a_x + i Im(M[y][y]) a_y ; coef(y, x) -> (re, im) register names"""
+            tx, ty_ = T[y]
+            first = True
+            for x in range(4):
+                if x == y:
+                    continue
+                mr, mi = coef(y, x)
+                ax, ay = self.re(xs[x]), self.im(xs[x])
+                if first:
+                    self.emit('mul.%s %s, %s, %s;' % (ty, tx, mr, ax))
+                    self.emit('mul.%s %s, %s, %s;' % (ty, ty_, mr, ay))
+                    first = False
+                else:
+                    self.emit('fma.rn.%s %s, %s, %s, %s;' % (ty, tx, mr, ax, tx))
+                    self.emit('fma.rn.%s %s, %s, %s, %s;' % (ty, ty_, mr, ay, ty_))
+                self.emit('neg.%s ngt, %s;' % (ty, mi))      # single-use negation: folds into the FMA operand
+                self.emit('fma.rn.%s %s, ngt, %s, %s;' % (ty, tx, ay, tx))
+                self.emit('fma.rn.%s %s, %s, %s, %s;' % (ty, ty_, mi, ax, ty_))
+            di = coef(y, y)[1]
+            self.emit('neg.%s ngt, %s;' % (ty, di))
+            self.emit('fma.rn.%s %s, ngt, %s, %s;' % (ty, tx, self.im(xs[y]), tx))
+            self.emit('fma.rn.%s %s, %s, %s, %s;' % (ty, ty_, di, self.re(xs[y]), ty_))
+
+        def gen2_temps(ngroups):
+            t = self.tmp()
+            T = [[('h%d_%dx_%d' % (g, y, t), 'h%d_%dy_%d' % (g, y, t)) for y in range(4)] for g in range(ngroups)]
+            for g in T:
+                for a, b in g:
+                    self.temps.add(a); self.temps.add(b)
+            return T
+
+        def gen2_family(pred):
+            # complex64: all 32 coefficients in registers, the predicated entry substitutes the identity and joins
+            # the plain body.  complex128 would spill that way: it loads one matrix row at a time and both entries
+            # run the same body with `ok` (always true for the plain entry) selecting the row or the identity row.
+            rowwise = ty == 'f64'
+            for k, (j1, j2) in enumerate(prs):
+                if j2 >= rb or not self.with_gen2: absent('GEN2'); continue
+                self.arm('A_GEN2%s%d' % ('P' if pred else '', k))
+                groups = gen2_groups(j1, j2)
+                if rowwise:
+                    if pred:
+                        self.compute_ok()
+                        self.emit('bra.uni B_GEN2_%d;' % k)
+                        continue
+                    self.emit('setp.eq.u32 ok, 0, 0;')
+                    self.label('B_GEN2_%d' % k)
+                    T = gen2_temps(len(groups))
+                    for y in range(4):
+                        self.ld4(('e0', 'e1', 'e2', 'e3'), 8 * y * self.esz)
+                        self.ld4(('e4', 'e5', 'e6', 'e7'), (8 * y + 4) * self.esz)
+                        for i in range(8):
+                            self.emit('selp.%s e%d, e%d, %s, ok;' % (ty, i, i, self.one() if i == 2 * y else self.zero()))
+                        for g, xs in enumerate(groups):
+                            gen2_row(y, xs, T[g], lambda yy, x: ('e%d' % (2 * x), 'e%d' % (2 * x + 1)))
+                        self.emit('mov.%s e%d, e%d;' % (ty, 8 + y, 2 * y))          # keep Re M[y][y] for the final step
+                    for g, xs in enumerate(groups):
+                        for y in range(4):
+                            self.emit('fma.rn.%s %s, e%d, %s, %s;' % (ty, self.re(xs[y]), 8 + y, self.re(xs[y]), T[g][y][0]))
+                            self.emit('fma.rn.%s %s, e%d, %s, %s;' % (ty, self.im(xs[y]), 8 + y, self.im(xs[y]), T[g][y][1]))
+                    self.done_arm()
+                    continue
+                if pred:
+                    self.compute_ok()
+                for q in range(8):
+                    self.ld4(tuple('e%d' % (4 * q + i) for i in range(4)), 4 * q * self.esz)
+                if pred:
+                    for i in range(32):
+                        diag = (i % 2 == 0) and ((i // 2) // 4 == (i // 2) % 4)
+                        self.emit('selp.%s e%d, e%d, %s, ok;' % (ty, i, i, self.one() if diag else self.zero()))
+                    self.emit('bra.uni B_GEN2_%d;' % k)
+                else:
+                    self.label('B_GEN2_%d' % k)
+                    for xs in groups:
+                        T = gen2_temps(1)[0]
+                        for y in range(4):
+                            gen2_row(y, xs, T, lambda yy, x: ('e%d' % (2 * (4 * yy + x)), 'e%d' % (2 * (4 * yy + x) + 1)))
+                        for y in range(4):
+                            dr = 'e%d' % (2 * (5 * y))
+                            self.emit('fma.rn.%s %s, %s, %s, %s;' % (ty, self.re(xs[y]), dr, self.re(xs[y]), T[y][0]))
+                            self.emit('fma.rn.%s %s, %s, %s, %s;' % (ty, self.im(xs[y]), dr, self.im(xs[y]), T[y][1]))
+                    self.done_arm()
+        gen2_family(False)
+        gen2_family(True)
         body = self.lines[body_start:]
         self.lines = self.lines[:body_start]
         return body
@@ -381,6 +478,9 @@ class Gen:
         head.append('.reg .b64 tt;')
         head.append('.reg .pred ok, pt;')
         head.append('.reg .%s c0, c1, c2, c3, c4, c5, c6, c7, n1, n3, n5, n7, sw;' % ty)
+        if self.with_gen2:
+            head.append('.reg .%s %s;' % (ty, ', '.join('e%d' % i for i in range(32))))
+            head.append('.reg .%s ngt;' % ty)
         temps = sorted(self.temps)
         for i in range(0, len(temps), 8):
             head.append('.reg .%s %s;' % (ty, ', '.join(temps[i:i + 8])))
@@ -411,8 +511,8 @@ class Gen:
         head.append('brx.idx.uni cls, TBL;')
         tail = ['L_DONE:']
         out = []
-        out.append('__device__ __forceinline__ void run_sweep_ops(%s (&a)[%d], %s &ph, uint32_t ops_smem, uint32_t pool_smem,'
-                   % (cxx_t, self.nx, cxx_t))
+        out.append('__device__ __forceinline__ void %s(%s (&a)[%d], %s &ph, uint32_t ops_smem, uint32_t pool_smem,'
+                   % (fname, cxx_t, self.nx, cxx_t))
         out.append('                                              uint32_t base, uint64_t outer_ok) {')
         out.append('    asm volatile("{\\n\\t"')
         for l in head + body + tail:
@@ -429,8 +529,15 @@ class Gen:
 def main():
     f32 = Gen('f32', 4)
     d64 = Gen('f64', 3)
-    o1, n1 = f32.render('f', 'float2', 'f')
-    o2, n2 = d64.render('d', 'double2', 'd')
+    o1, n1 = f32.render('run_sweep_ops_dense2', 'float2', 'f')
+    o2, n2 = d64.render('run_sweep_ops_dense2', 'double2', 'd')
+    # the lean interpreter: the same arms without the dense two-target family (sweeps that hold no such op use
+    # it; with the 4x4 arms in the same block the common arms lost ~3 % on the headline circuit)
+    l32 = Gen('f32', 4, with_gen2=False)
+    l64 = Gen('f64', 3, with_gen2=False)
+    o3, n3 = l32.render('run_sweep_ops', 'float2', 'f')
+    o4, n4 = l64.render('run_sweep_ops', 'double2', 'd')
+    assert n3 == n1 and n4 == n1
     assert n1 == n2 and f32.labels.index('A_END') == d64.labels.index('A_END')
     names = {}
     for i, l in enumerate(f32.labels):
@@ -444,16 +551,17 @@ def main():
               ('ARM_GEN_P', 'A_GENP0'), ('ARM_GENM', 'A_GENM0'), ('ARM_CX', 'A_CX0_1'), ('ARM_PH1', 'A_PH10'),
               ('ARM_PH1_P', 'A_PH1P0'), ('ARM_SGN1', 'A_SGN10'), ('ARM_SGN1_P', 'A_SGN1P0'), ('ARM_PH2', 'A_PH20'),
               ('ARM_PH2_P', 'A_PH2P0'), ('ARM_SGN2', 'A_SGN20'), ('ARM_SGN2_P', 'A_SGN2P0'), ('ARM_PHT', 'A_PHT'),
-              ('ARM_PHM', 'A_PHM'), ('ARM_END', 'A_END')]
+              ('ARM_PHM', 'A_PHM'), ('ARM_END', 'A_END'), ('ARM_GEN2', 'A_GEN20'), ('ARM_GEN2_P', 'A_GEN2P0')]
+    # (ids come from the full table; the lean table has the same length)
     for c, l in consts:
         print('constexpr int %s = %d;' % (c, f32.labels.index(l)))
     print('constexpr int ARM_COUNT = %d;' % n1)
     print('__host__ __device__ constexpr int cx_arm(int j, int cb) { return ARM_CX + j * 3 + (cb < j ? cb : cb - 1); }')
     print('constexpr int OUTER_SLOT_NONE = 63;   // bit 63 of the tile-level predicate mask is always 1')
     print()
-    print('\n'.join(o1))
-    print()
-    print('\n'.join(o2))
+    for o in (o3, o4, o1, o2):
+        print('\n'.join(o))
+        print()
 
 
 if __name__ == '__main__':

@@ -51,7 +51,8 @@ constexpr int SWEEP_REG = 0, SWEEP_GENERIC = 1;
 struct Sweep {
     int32_t kind, first, count, nreg;
     int8_t rpos[REG_BITS_MAX];       // tile-local positions of the register bits, ascending
-    int32_t thread_phase;            // some PHASE op of the sweep is uniform over a thread's amplitudes
+    int16_t thread_phase;            // some PHASE op of the sweep is uniform over a thread's amplitudes
+    int16_t has_dense2;              // the sweep holds a dense two-target register op (GEN2 arms)
     // host-precomputed addressing of the compile-time-geometry path: inserting a zero at rpos[j] is
     // x += x & himask[j]; stride[j] = padded shared-memory distance in bytes between the two values of bit j
     uint32_t himask[REG_BITS_MAX];

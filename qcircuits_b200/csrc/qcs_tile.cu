@@ -111,7 +111,7 @@ __device__ __forceinline__ void apply_generic(typename CxT<R>::T *tile, int m, c
 //    into the cheapest exact form, and common scalar factors (1/sqrt2 of H, cos of RX) are deferred into the
 //    pass-level factor that the final store applies anyway;
 //  * every position that selects registers (target bit, control bit, phase bits) is baked into the arm.
-// Instructions per thread (complex64, 16 amplitudes): HAD 32, REALU / IMAGU 48, REAL / IMAG 64, GEN 128,
+// Instructions per thread (complex64, 16 amplitudes): HAD 32, REALU / IMAGU 48, REAL / IMAG 64, GEN 128, GEN2 256,
 // PH1 32, SGN1 16, PH2 16, SGN2 8, CX 24 (moves), PHT 4; + ~9 per op for fetch and dispatch.  The loop is
 // software-pipelined: the record of op i+1 and the coefficients of op i are in flight during the dispatch.
 // Predicates that do not involve register bits (control bits elsewhere in the tile / outside the tile) are
@@ -154,7 +154,8 @@ __device__ __forceinline__ void reg_sweep_fast(typename CxT<R>::T *tile, const S
         for (int x = 0; x < NX; ++x) a[x] = *reinterpret_cast<const C *>(__cvta_shared_to_generic(addr[x]));
     }
     C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
-    run_sweep_ops(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
+    if (sw.has_dense2) run_sweep_ops_dense2(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
+    else run_sweep_ops(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
     if (sw.thread_phase) {
 #pragma unroll
         for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
@@ -228,7 +229,8 @@ __device__ __forceinline__ void reg_sweep(typename CxT<R>::T *tile, int m_rt, co
                 if (FAST || x < nx_used) a[x] = tile[addr[x]];
         }
         C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
-        run_sweep_ops(a, ph, ops_smem, pool_smem, base, outer_ok);
+        if (sw.has_dense2) run_sweep_ops_dense2(a, ph, ops_smem, pool_smem, base, outer_ok);
+        else run_sweep_ops(a, ph, ops_smem, pool_smem, base, outer_ok);
         if (sw.thread_phase) {
 #pragma unroll
             for (uint32_t x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
@@ -804,7 +806,9 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         if (n < 64 && (o.ctrl_mask >> n)) return set_error(QCS_ERR_ARG, "control bit out of range");
         if (o.kind == QCS_OP_DENSE) {
             dense_mask |= seen;
-            hop[i].kind = o.k == 1 ? 0 : 2;
+            // 0: one target (register op), 3: two targets, few controls (register op on a pair of register
+            // bits when both fit), 2: everything else dense (shared-memory op)
+            hop[i].kind = o.k == 1 ? 0 : (o.k == 2 && __builtin_popcountll(o.ctrl_mask) <= 2 ? 3 : 2);
             hop[i].nd_mask = seen;
             hop[i].d_mask = o.ctrl_mask;
         } else if (o.kind == QCS_OP_DIAG) {
@@ -896,6 +900,11 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     // ---- sweeps: greedy, commuting ops may overtake ops that wait for a later sweep --------------------
     const int rb = c64 ? REG_BITS_C64 : REG_BITS_C128;
     const int nreg = rb < m ? rb : m;
+    bool any_dense2 = false;
+    for (int i = 0; i < nops; ++i) {
+        if (hop[i].kind == 3 && (nreg < 2 || tune_int("QCS_NO_DENSE2_REG", 0))) hop[i].kind = 2;
+        any_dense2 |= hop[i].kind == 3;
+    }
     int pending[QCS_MAX_OPS];
     int npend = nops;
     for (int i = 0; i < nops; ++i) pending[i] = i;
@@ -929,9 +938,10 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         uint32_t S_local = 0;                  // tile-local mask of the register bits
         int S_count = 0;
         int taken[QCS_MAX_OPS], ntaken = 0, rest[QCS_MAX_OPS], nrest = 0;
+        uint32_t S_forbid = 0;                 // control bits of the taken two-target ops: must stay thread bits
         auto select = [&](uint32_t fixed, uint32_t &S_out, int &S_cnt, int *tk, int &ntk, int *rs, int &nrs) -> int {
             uint64_t blk_nd = 0, blk_d = 0;
-            uint32_t S = fixed;
+            uint32_t S = fixed, forbid = 0;
             int cnt = __builtin_popcount(fixed), score = 0;
             ntk = nrs = 0;
             for (int i = 0; i < npend; ++i) {
@@ -941,18 +951,28 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 if (can && h.kind == 0) {
                     const uint32_t tbit = 1u << local_of(ops[idx].bitpos[0]);
                     if (!(S & tbit)) {
-                        if (!fixed && cnt < nreg) { S |= tbit; ++cnt; }
+                        if (!fixed && cnt < nreg && !(forbid & tbit)) { S |= tbit; ++cnt; }
                         else can = false;
                     }
+                } else if (can && h.kind == 3) {
+                    const uint32_t tb = (1u << local_of(ops[idx].bitpos[0])) | (1u << local_of(ops[idx].bitpos[1]));
+                    const uint32_t cl = local_mask(ops[idx].ctrl_mask & tile_mask);
+                    const uint32_t need = tb & ~S;
+                    if ((cl & (S | tb)) || (need & forbid) || __builtin_popcount(forbid | cl) > m - nreg) can = false;
+                    else if (need) {
+                        if (!fixed && cnt + __builtin_popcount(need) <= nreg) { S |= need; cnt += __builtin_popcount(need); }
+                        else can = false;
+                    }
+                    if (can) forbid |= cl;
                 }
-                if (can) { tk[ntk++] = idx; score += h.kind == 0 ? 16 : 1; }
+                if (can) { tk[ntk++] = idx; score += h.kind == 1 ? 1 : 16; }
                 else { rs[nrs++] = idx; blk_nd |= h.nd_mask; blk_d |= h.d_mask; }
             }
-            S_out = S; S_cnt = cnt;
+            S_out = S; S_cnt = cnt; S_forbid = forbid;
             return score;
         };
         int best_score = select(0u, S_local, S_count, taken, ntaken, rest, nrest);
-        if (nreg >= 2 && tune_int("QCS_SWEEP_SEARCH", 1)) {
+        if (nreg >= 2 && !any_dense2 && tune_int("QCS_SWEEP_SEARCH", 1)) {
             // alternatives: register sets drawn from the first distinct dense targets still pending (always with
             // the first one, so that the sweep makes progress); keep the set that absorbs the most ops
             int cand[8], ncand = 0;
@@ -988,11 +1008,12 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             const uint32_t bm = ((1u << nreg) - 1u) << (blk * nreg);
             if (!(S_local & bm)) continue;
             for (int b = blk * nreg; b < (blk + 1) * nreg && b < m && S_count < nreg; ++b)
-                if (!(S_local & (1u << b))) { S_local |= 1u << b; ++S_count; }
+                if (!((S_local | S_forbid) & (1u << b))) { S_local |= 1u << b; ++S_count; }
         }
         for (int b = m - 1; b >= 0 && S_count < nreg; --b)
-            if (!(S_local & (1u << b))) { S_local |= 1u << b; ++S_count; }
-        sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg; sw.thread_phase = 0;
+            if (!((S_local | S_forbid) & (1u << b))) { S_local |= 1u << b; ++S_count; }
+        if (S_count < nreg) return set_error(QCS_ERR_UNSUPPORTED, "no free tile bit left for the register set");
+        sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg; sw.thread_phase = 0; sw.has_dense2 = 0;
         int8_t reg_index_of_local[32];
         for (int j = 0; j < REG_BITS_MAX; ++j) { sw.rpos[j] = 0; sw.himask[j] = 0; sw.stride[j] = 0; }
         for (int b = 0, j = 0; b < 32; ++b) {
@@ -1040,7 +1061,33 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         for (int t = 0; t < ntaken; ++t) {
             const qcs_op &o = ops[taken[t]];
             if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
-            if (hop[taken[t]].kind == 0) {
+            if (hop[taken[t]].kind == 3) {
+                // dense two-target op on the register pair (j1 < j2); the arm indexes the 4x4 matrix by
+                // (bit j2 : bit j1), so swap the index bits when the matrix's first qubit sits on j1
+                RegOp &r = P.regops[P.nregops++];
+                const int r0 = reg_index_of_local[local_of(o.bitpos[0])], r1 = reg_index_of_local[local_of(o.bitpos[1])];
+                if (r0 < 0 || r1 < 0) return set_error(QCS_ERR_UNSUPPORTED, "two-target op outside the register set");
+                if (!split_masks(o.ctrl_mask, o.ctrl_mask, r))
+                    return set_error(QCS_ERR_UNSUPPORTED, "too many distinct tile-level predicates");
+                if (r.reg_care) return set_error(QCS_ERR_UNSUPPORTED, "two-target op with a register-bit control");
+                const int j1 = r0 < r1 ? r0 : r1, j2 = r0 < r1 ? r1 : r0;
+                static const int pair_index2[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+                const bool swap_idx = r0 == j1;
+                double cf2[32];
+                for (int y = 0; y < 4; ++y)
+                    for (int x = 0; x < 4; ++x) {
+                        const int ys = swap_idx ? ((y & 1) << 1) | (y >> 1) : y, xs = swap_idx ? ((x & 1) << 1) | (x >> 1) : x;
+                        cf2[2 * (4 * y + x)] = o.matrix[2 * (4 * ys + xs)];
+                        cf2[2 * (4 * y + x) + 1] = o.matrix[2 * (4 * ys + xs) + 1];
+                    }
+                const bool pred = r.base_care != 0 || r.outer_slot != OUTER_SLOT_NONE;
+                r.code = (uint16_t)((pred ? ARM_GEN2_P : ARM_GEN2) + pair_index2[j1][j2]);
+                sw.has_dense2 = 1;
+                const int at = push_reals(cf2, 32);
+                if (at < 0) return set_error(QCS_ERR_UNSUPPORTED, "fused pass matrix pool exhausted");
+                r.mat = at * (int)csize;
+                ++sw.count;
+            } else if (hop[taken[t]].kind == 0) {
                 RegOp &r = P.regops[P.nregops++];
                 const int j = reg_index_of_local[local_of(o.bitpos[0])];
                 const double *M = o.matrix;   // m00 m01 m10 m11 as (re, im)

@@ -3,9 +3,10 @@
 Random fused passes are built from gate kinds chosen to reach each arm family -- H (HAD), real matrices
 (REAL / REALU), RX / Y (IMAG / IMAGU), arbitrary and non-unitary 2x2 (GEN), the same under controls that fall
 on register bits (CX, GENM) or elsewhere (the "_P" entries), phases and signs on one or two register bits
-(PH1 / SGN1 / PH2 / SGN2, plain and predicated), thread-uniform phases (PHT) and general diagonal patterns
-(PHM).  `qcs_plan_stats` reports which arms each pass uses; the test asserts that the union covers the whole
-jump table for the amplitude type, so no arm can be wrong without a parity failure here."""
+(PH1 / SGN1 / PH2 / SGN2, plain and predicated), thread-uniform phases (PHT), general diagonal patterns
+(PHM) and dense two-qubit matrices on a pair of register bits (GEN2, plain and predicated).
+`qcs_plan_stats` reports which arms each pass uses; the test asserts that the union covers the whole jump
+table for the amplitude type, so no arm can be wrong without a parity failure here."""
 import ctypes
 
 import numpy as np
@@ -24,7 +25,7 @@ FAMILIES = [('HAD', 0, 'j'), ('REAL', 4, 'j'), ('REAL_P', 8, 'j'), ('REALU', 12,
             ('IMAG_P', 20, 'j'), ('IMAGU', 24, 'j'), ('GEN', 28, 'j'), ('GEN_P', 32, 'j'), ('GENM', 36, 'j'),
             ('CX', 40, 'jc'), ('PH1', 52, 'j'), ('PH1_P', 56, 'j'), ('SGN1', 60, 'j'), ('SGN1_P', 64, 'j'),
             ('PH2', 68, 'p'), ('PH2_P', 74, 'p'), ('SGN2', 80, 'p'), ('SGN2_P', 86, 'p'), ('PHT', 92, '1'),
-            ('PHM', 93, '1'), ('END', 94, '1')]
+            ('PHM', 93, '1'), ('END', 94, '1'), ('GEN2', 95, 'p'), ('GEN2_P', 101, 'p')]
 PAIRS = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
 
 
@@ -67,7 +68,7 @@ def random_gate(rng):
     Y = np.array([[0, -1j], [1j, 0]])
     Z = np.diag([1.0 + 0j, -1.0])
     ph = lambda: np.diag([1.0, np.exp(1j * rng.uniform(0, 2 * np.pi))])
-    kind = int(rng.integers(24))
+    kind = int(rng.integers(28))
     if kind == 0: return H
     if kind == 1: return X
     if kind == 2: return rng.normal(size=(2, 2)).astype(np.complex128)              # real, non-unitary: REAL
@@ -91,7 +92,11 @@ def random_gate(rng):
     if kind == 20: return np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, size=4)))      # 2-qubit diagonal: PHM ...
     if kind == 21: return np.diag(rng.uniform(0.5, 1.5, size=2)).astype(np.complex128) # real non-unitary diagonal
     if kind == 22: return _ctrl(np.diag([1.0 + 0j, rng.uniform(0.5, 1.5)]))            # controlled real factor
-    return _ctrl(H)                                                                    # REAL_P / GENM
+    if kind == 23: return _ctrl(H)                                                     # REAL_P / GENM
+    if kind == 24: return rand_unitary(rng, 2)                                         # GEN2 (or the shared-memory dense op)
+    if kind == 25: return _ctrl(rand_unitary(rng, 2))                                  # GEN2_P
+    if kind == 26: return rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))       # GEN2, non-unitary
+    return _ctrl(rand_unitary(rng, 2), 2)                                              # GEN2_P, two controls
 
 
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
@@ -122,7 +127,7 @@ def test_every_interpreter_arm_matches_the_oracle(dtype):
         rc = lib.qcs_plan_stats(n, code, ops, len(ops), stats)
         if rc != 0:          # (more high dense bits than one tile holds: not a pass the scheduler would build)
             continue
-        seen |= {a for a in range(100) if stats[8 + a]}
+        seen |= {a for a in range(112) if stats[8 + a]}
         s = qc.State.from_column_vector(vec, dtype=dtype)
         out = s._dv.apply_ops(ops, keep)
         got = out.to_host()                          # normalised by the fused squared norm
