@@ -212,6 +212,34 @@ def merge_single_qubit_gates(gates):
     return out
 
 
+def build_passes(gates, groups, n, dtype):
+    """ctypes op arrays for the scheduled groups, each checked against the engine's pass planner
+    (qcs_plan_stats plans without launching and needs no device).  A group the planner cannot hold in one
+    pass -- too many register ops, sweeps or coefficients for its tables, which the scheduler only
+    estimates -- is split in halves until it fits; a single op always does.
+    Returns [(ops, keepalive, gate count)]."""
+    lib = _lib.load()
+    code = _lib.dtype_code(dtype)
+    stats = (ctypes.c_int32 * 128)()
+    out = []
+
+    def emit(group):
+        ops, keep = make_ops([(gates[i].plan, gates[i].bits, False) for i in group])
+        rc = lib.qcs_plan_stats(n, code, ops, len(ops), stats)
+        if rc == 0 or len(group) == 1:
+            if rc != 0:
+                _lib.check(rc)
+            out.append((ops, keep, len(group)))
+            return
+        half = len(group) // 2
+        emit(group[:half])
+        emit(group[half:])
+
+    for group in groups:
+        emit(list(group))
+    return out
+
+
 class Circuit:
     """An ordered list of gates on ``n`` qubits.
 
@@ -256,8 +284,7 @@ class Circuit:
                 if g0.wide:
                     comp.append(('dense', g0))
                 else:
-                    ops, keep = make_ops([(gates[i].plan, gates[i].bits, False) for i in group])
-                    comp.append(('tile', ops, keep, len(group)))
+                    comp.extend(('tile', ops, keep, cnt) for ops, keep, cnt in build_passes(gates, [group], self.n, dtype))
             self._plans[key] = comp
         return comp
 

@@ -200,11 +200,11 @@ class CudaEngine:
             _lib.check(lib.qcs_set_basis(self.buf.data_ptr(), self.n_local, self.code, index, _lib.stream_ptr()))
 
     def run_local(self, rank_gates, max_ops):
-        from ._device import make_ops
+        from .circuit import build_passes
         lib = _lib.load()
         ws = _lib.workspace().data_ptr()
-        for group in schedule_passes(rank_gates, self.n_local, self.dtype, max_ops=max_ops):
-            ops, keep = make_ops([(rank_gates[i].plan, rank_gates[i].bits, False) for i in group])
+        groups = schedule_passes(rank_gates, self.n_local, self.dtype, max_ops=max_ops)
+        for ops, keep, _ in build_passes(rank_gates, groups, self.n_local, self.dtype):
             _lib.check(lib.qcs_apply_fused(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, ops,
                                            len(ops), None, None, ws, _lib.stream_ptr()))
             self.launches += 1

@@ -48,3 +48,24 @@ def test_tile_shrinks_its_contiguous_run_for_many_high_targets():
     ops, keep = make_ops([(_gates.analyze(H), [b], False) for b in range(10, 26)])
     out = (ctypes.c_int32 * 128)()
     assert lib.qcs_plan_stats(26, 0, ops, len(ops), out) == -3      # QCS_ERR_UNSUPPORTED: too many high bits
+
+
+def test_groups_the_planner_cannot_hold_are_split():
+    """A pass the scheduler accepts by count but whose register-op table would overflow (general 4-qubit
+    diagonal gates: 15 phase patterns each) is split until every piece plans."""
+    import qcircuits_b200 as qc
+    from qcircuits_b200.circuit import Circuit, build_passes, merge_single_qubit_gates, schedule_passes
+    rng = np.random.default_rng(3)
+    n = 16
+    c = Circuit(n)
+    for _ in range(60):
+        d = np.exp(1j * rng.uniform(0, 2 * np.pi, size=16))
+        c.append(qc.Operator.from_matrix(np.diag(d)), [int(q) for q in rng.permutation(n)[:4]])
+    gates = merge_single_qubit_gates(c.gates)
+    groups = schedule_passes(gates, n, np.complex64, max_ops=128)
+    passes = build_passes(gates, groups, n, np.complex64)
+    assert sum(cnt for _, _, cnt in passes) == 60
+    assert len(passes) > len(groups)                 # 60 x 15 patterns do not fit one 420-entry table
+    st = (ctypes.c_int32 * 128)()
+    for ops, keep, cnt in passes:
+        assert _lib.load().qcs_plan_stats(n, 0, ops, len(ops), st) == 0
