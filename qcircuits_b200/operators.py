@@ -3,11 +3,13 @@ qcircuits/operators.py.
 
 Gate tensors are parameters (at most 2^22 entries in any configuration), so they stay host
 NumPy arrays; Operator-on-Operator composition (operators.py:225-278 with an OperatorBase
-argument) is host arithmetic.  What changes is Operator-on-State and Operator-on-DensityOperator:
+argument) is host arithmetic for small operators and a device gate pass over the out-wires from
+8 qubits up (``Operator._compose_on_device``).  What changes is Operator-on-State and Operator-on-DensityOperator:
 those no longer run ``np.tensordot`` over the rank-n tensor but call the sm_100a kernels of
 libqcs (qcs_apply_fused / qcs_apply_dense) on the device buffer, with the reference's
 renormalise-after-every-gate folded into the same pass (see include/qcs.h, "lazy normalisation").
 """
+import os
 from itertools import product
 
 import numpy as np
@@ -103,6 +105,17 @@ def _validated_indices(op_qubits, d, qubit_indices):
     return qubit_indices
 
 
+DEVICE_COMPOSE_MIN_BITS = 16      # operator-on-operator composition runs on the device from 8 qubits up
+
+
+def _cuda_ready():
+    from . import _lib
+    try:
+        return bool(_lib.torch().cuda.is_available()) and os.path.exists(_lib.LIB_PATH)
+    except Exception:
+        return False
+
+
 class Operator(OperatorBase):
     """An operator on the state space of d qubits: a rank-2d tensor, axes (out0, in0, out1, in1, ...)."""
 
@@ -146,6 +159,8 @@ class Operator(OperatorBase):
         d = arg.rank // 2
         k = self.rank // 2
         qi = _validated_indices(k, d, qubit_indices)
+        if 2 * d >= DEVICE_COMPOSE_MIN_BITS and _cuda_ready():
+            return self._compose_on_device(arg, qi)
         order = qi + sorted(set(range(d)) - set(qi))
         moved = np.transpose(arg._t, _pair_axes(order))
         out = np.tensordot(self._t, moved, (list(range(1, 2 * k, 2)), list(range(0, 2 * k, 2))))
@@ -153,6 +168,24 @@ class Operator(OperatorBase):
         back = np.concatenate([np.arange(2 * k).reshape(2, k).T.reshape(-1), np.arange(2 * k, 2 * d)])
         result = arg.__class__(np.transpose(out, back))
         return result.permute_qubits(order, inverse=True)
+
+    def _compose_on_device(self, arg, qi):
+        """A(B) for a large operator-shaped B: the rank-2d tensor of B is a flat vector of 2d bits
+        in which the out-wire of qubit q is flat bit 2(d-1-q)+1 (the row bits of the density-operator layout),
+        so the composition is the ordinary gate pass of this operator on those bits -- the tile engine for up to
+        4 target qubits, the dense path above (e.g. the 10-qubit Hadamard of examples/grover_algorithm.py:41).
+        complex128, no renormalisation (operators.py:275 renormalises states only)."""
+        from ._device import DeviceVector, make_ops
+        d = arg.rank // 2
+        dv = DeviceVector.from_host(arg._t, np.complex128)
+        bits = [2 * (d - 1 - q) + 1 for q in qi]
+        plan = self._plan()
+        if len(plan.targets) <= 4:
+            ops, keep = make_ops([(plan, bits, False)])
+            out = dv.apply_ops(ops, keep, track_norm=False)
+        else:
+            out = dv.apply_dense(self._device_matrix(np.complex128), plan.k, bits, track_norm=False)
+        return arg.__class__(out.to_host().reshape([2] * (2 * d)))
 
     def _apply(self, arg, qubit_indices=None):
         if isinstance(arg, State):

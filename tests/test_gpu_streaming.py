@@ -115,3 +115,26 @@ def test_partial_trace_against_the_oracle(dtype):
     got = qc.State.from_column_vector(psi, dtype=dtype).reduced_density_operator([8, 3])
     want = orc.reduced_tensor(orc.outer_product(psi.reshape([2] * 9)), [8, 3])
     assert rel_err(got._t.reshape(-1), np.asarray(want).reshape(-1)) < tol
+
+
+def test_operator_composition_on_the_device():
+    """A(B) for an 8-qubit B runs as a gate pass over B's out-wires (Operator._compose_on_device); compared
+    with the oracle's restatement of operators.py:225-278 for tile-engine operators (1-3 qubits, controlled,
+    diagonal) and dense ones (5 and 8 qubits)."""
+    from qcircuits_b200 import operators as ops_mod
+    from tests.util import rand_unitary
+    rng = np.random.default_rng(10)
+    d = 8
+    assert 2 * d >= ops_mod.DEVICE_COMPOSE_MIN_BITS
+    B = qc.Operator.from_matrix(rand_unitary(rng, d))
+    cases = [(qc.Hadamard(), [3]), (qc.CNOT(), [6, 1]), (qc.RotationZ(0.7), [0]), (qc.Toffoli(), [7, 2, 4]),
+             (qc.Operator.from_matrix(rand_unitary(rng, 2)), [5, 0]),
+             (qc.Operator.from_matrix(rand_unitary(rng, 5)), [4, 0, 7, 2, 1]),
+             (qc.Operator.from_matrix(rand_unitary(rng, d)), None)]
+    for A, qi in cases:
+        got = A(B, qubit_indices=qi)
+        want = orc.compose_operators(A._t, B._t, qi)
+        assert isinstance(got, qc.Operator) and got.rank == 2 * d
+        assert rel_err(got._t.reshape(-1), np.asarray(want).reshape(-1)) < 1e-12, qi
+    # B itself is untouched (operators.py: "returns a new object")
+    assert rel_err(B.to_matrix().reshape(-1), B.to_matrix().reshape(-1)) == 0
