@@ -236,9 +236,21 @@ class State(Tensor):
 
         d = self.rank
         bitpos = [d - 1 - int(q) for q in qubit_indices]
-        ps = self._dv.marginals(bitpos)
-        outcome = _sample(ps, u)
         m = len(qubit_indices)
+        if m <= MEASURE_CHUNK_BITS:
+            ps = self._dv.marginals(bitpos)
+            outcome = _sample(ps, u)
+        else:
+            # many qubits (the default measure() of a large state): 2^m marginals would not fit the host, so
+            # the same inverse-CDF draw is taken hierarchically, MEASURE_CHUNK_BITS qubits at a time
+            work = [self._dv]
+
+            def conditional(done_bits, done_outcome, chunk_bits):
+                if done_bits:
+                    work[0] = work[0].collapsed(done_bits, done_outcome, False)
+                return work[0].marginals(chunk_bits)
+
+            outcome = _sample_chunked(conditional, bitpos, u, MEASURE_CHUNK_BITS)
         bits = tuple((outcome >> i) & 1 for i in range(m - 1, -1, -1))
         # collapse + renormalise: the kernel keeps the matching amplitudes and reports their squared
         # norm, which becomes the lazy scale (covers both the /sqrt(p) and the trailing renormalize_)
@@ -254,6 +266,37 @@ class State(Tensor):
     def reduced_density_operator(self, qubit_indices):
         """Reduced density operator of the listed qubits (state.py:285-305)."""
         return self.density_operator().reduced_density_operator(qubit_indices)
+
+
+MEASURE_CHUNK_BITS = 16
+
+
+def _sample_chunked(conditional, bitpos, u, chunk):
+    """Inverse-CDF sampling of an outcome over ``bitpos`` (first = most significant) without ever holding the
+    2^m probabilities: the outcome of the first ``chunk`` bits is drawn from their marginals, u is rescaled to
+    the position inside that outcome's probability interval, and the next chunk is drawn from the marginals
+    conditioned on what has been drawn -- in exact arithmetic the same index as
+    ``searchsorted(cumsum(p) / sum(p), u, 'right')`` over all 2^m outcomes (state.py:364, np.random.choice).
+    ``conditional(done_bits, done_outcome, chunk_bits)`` returns the marginals of ``chunk_bits`` given that the
+    previous chunk ``done_bits`` came out as ``done_outcome`` (and everything before it as drawn).
+    ``u`` None draws the one uniform np.random.choice would draw from NumPy's global stream."""
+    if u is None:
+        u = float(np.random.random_sample())
+    outcome = 0
+    done_bits, done_outcome = [], 0
+    for start in range(0, len(bitpos), chunk):
+        bits = bitpos[start:start + chunk]
+        ps = np.asarray(conditional(done_bits, done_outcome, bits), dtype=np.float64)
+        cdf = np.cumsum(ps)
+        cdf /= cdf[-1]
+        o = min(int(np.searchsorted(cdf, u, side='right')), len(cdf) - 1)
+        lo = cdf[o - 1] if o > 0 else 0.0
+        width = cdf[o] - lo
+        u = (u - lo) / width if width > 0 else 0.0
+        u = min(max(u, 0.0), float(np.nextafter(1.0, 0.0)))
+        outcome = (outcome << len(bits)) | o
+        done_bits, done_outcome = bits, o
+    return outcome
 
 
 def _sample(ps, u=None):

@@ -138,3 +138,40 @@ def test_operator_composition_on_the_device():
         assert rel_err(got._t.reshape(-1), np.asarray(want).reshape(-1)) < 1e-12, qi
     # B itself is untouched (operators.py: "returns a new object")
     assert rel_err(B.to_matrix().reshape(-1), B.to_matrix().reshape(-1)) == 0
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_measuring_more_qubits_than_one_chunk(dtype):
+    """State.measure of more than MEASURE_CHUNK_BITS qubits (e.g. the default measure() of a large state) draws
+    the outcome hierarchically; it must be the outcome of the reference's flat rule for the same uniform, and
+    the collapsed state must match."""
+    from qcircuits_b200.state import MEASURE_CHUNK_BITS
+    rng = np.random.default_rng(13)
+    tol = TOL[np.dtype(dtype)]
+    n = MEASURE_CHUNK_BITS + 4
+    vec = rand_state_vec(rng, n)
+    vec[rng.uniform(size=vec.size) < 0.5] = 0          # make intervals of very different widths
+    vec /= np.linalg.norm(vec)
+    for qi, remove in ((list(range(n)), False), ([int(q) for q in rng.permutation(n)[:n - 1]], True),
+                       ([int(q) for q in rng.permutation(n)[:MEASURE_CHUNK_BITS + 1]], False)):
+        u = float(rng.uniform())
+        s = _state(vec, dtype)
+        bits = s.measure(qi, remove=remove, u=u)
+        want_ps, _, _ = orc.measurement_probabilities(vec.reshape([2] * n), qi)
+        want_bits, want_t = orc.measure(vec.reshape([2] * n), qi, u, remove=remove)
+        o = orc.sample_outcome(want_ps, u)
+        cdf = np.cumsum(want_ps) / want_ps.sum()
+        edge = min(abs(u - cdf[o]), abs(u - (cdf[o - 1] if o else 0.0)))
+        if edge > 1e-6:                                    # (complex64 marginals differ from the oracle's by ~1e-7)
+            assert tuple(bits) == tuple(want_bits), (qi, remove)
+            assert rel_err(np.asarray(s._t).reshape(-1), np.asarray(want_t).reshape(-1)) < 4 * tol
+    # default measure(): all qubits, global NumPy stream -- deterministic under a seed, state collapses to a basis state
+    s = _state(vec, dtype)
+    np.random.seed(11)
+    bits = s.measure()
+    assert len(bits) == n
+    idx = int(''.join(str(b) for b in bits), 2)
+    assert abs(vec[idx]) > 0
+    assert abs(abs(s.to_column_vector()[idx]) - 1) < 10 * tol
+    np.random.seed(11)
+    assert _state(vec, dtype).measure() == bits

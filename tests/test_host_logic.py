@@ -181,3 +181,50 @@ def test_workload_generator_matches_the_oracles():
     from qcircuits_b200.workloads import layered_gate_list
     for n, depth in ((3, 4), (12, 5), (30, 40)):
         assert layered_gate_list(n, depth, 1234) == orc.layered_circuit(n, depth, 1234)
+
+
+def test_chunked_sampling_equals_the_flat_inverse_cdf():
+    """State.measure of many qubits samples hierarchically (state._sample_chunked); the outcome must be the
+    index the reference's flat np.random.choice rule gives for the same uniform."""
+    from qcircuits_b200.state import _sample_chunked
+    rng = np.random.default_rng(12)
+    m = 11
+    for trial in range(40):
+        p = rng.uniform(size=2 ** m) ** 3
+        if trial % 3 == 0:
+            p[rng.uniform(size=2 ** m) < 0.7] = 0.0          # sparse distributions (basis-like states)
+        p /= p.sum()
+        t = p.reshape([2] * m)
+        order = [int(b) for b in rng.permutation(m)]         # measured bit positions, first = most significant
+        axes = [m - 1 - b for b in order]
+        flat = np.transpose(t, axes).reshape(-1)
+        state = {'t': t.copy()}
+
+        def conditional(done_bits, done_outcome, chunk_bits):
+            if done_bits:
+                sel = [slice(None)] * m
+                for j, b in enumerate(done_bits):
+                    sel[m - 1 - b] = (done_outcome >> (len(done_bits) - 1 - j)) & 1
+                kept = np.zeros_like(state['t'])
+                kept[tuple(sel)] = state['t'][tuple(sel)]
+                state['t'] = kept / kept.sum()
+            ax = [m - 1 - b for b in chunk_bits]
+            rest = tuple(a for a in range(m) if a not in ax)
+            return np.transpose(state['t'].sum(axis=rest), np.argsort(np.argsort(ax))).reshape(-1)
+
+        u = float(rng.uniform())
+        cdf = np.cumsum(flat)
+        cdf /= cdf[-1]
+        want = int(np.searchsorted(cdf, u, side='right'))
+        got = _sample_chunked(conditional, order, u, 4)
+        assert got == want, (trial, got, want)
+    # u = None consumes exactly one uniform of the global stream, like np.random.choice
+    np.random.seed(5)
+    expect_u = np.random.random_sample()
+    after = np.random.random_sample()
+    np.random.seed(5)
+    state = {'t': np.full([2] * 6, 1.0 / 64)}
+    m = 6
+    got = _sample_chunked(lambda db, do, cb: np.full(2 ** len(cb), 1.0 / 2 ** len(cb)), list(range(6)), None, 3)
+    assert got == int(expect_u * 64)
+    assert np.random.random_sample() == after
