@@ -566,6 +566,87 @@ __global__ void __launch_bounds__(EW_THREADS) outer_kernel(C *__restrict__ rho, 
     }
 }
 
+// ---- one-qubit gate as a pure streaming pass (operators.py:261 for a 2x2 operator) --------------------
+// North star (1): "high target qubits handled by strided 128-bit loads".  A pass that holds a single one-qubit
+// gate needs no shared-memory tile: a thread loads the two 16-byte vectors that differ in the target bit,
+// applies the 2x2 matrix (identity, still scaled by the lazy 1/sqrt(norm), where a control bit is 0) and stores
+// both -- four pairs in flight per thread.  For complex64 and target bit 0 the pair sits inside one vector.
+template <typename R> struct Gate1Args {
+    R m[8];                 // m00 m01 m10 m11 as (re, im)
+    uint64_t ctrl;          // flat-index control mask
+    int32_t n, tbit;
+};
+template <typename C> __device__ __forceinline__ void unpack_vec(const uint4 v, C (&a)[2]);
+template <> __device__ __forceinline__ void unpack_vec<float2>(const uint4 v, float2 (&a)[2]) {
+    a[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+    a[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+}
+template <> __device__ __forceinline__ void unpack_vec<double2>(const uint4 v, double2 (&a)[2]) {
+    a[0] = make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
+    a[1] = a[0];
+}
+__device__ __forceinline__ uint4 pack_vec(const float2 (&a)[2]) {
+    return make_uint4(__float_as_uint(a[0].x), __float_as_uint(a[0].y), __float_as_uint(a[1].x), __float_as_uint(a[1].y));
+}
+__device__ __forceinline__ uint4 pack_vec(const double2 (&a)[2]) {
+    return make_uint4(__double2loint(a[0].x), __double2hiint(a[0].x), __double2loint(a[0].y), __double2hiint(a[0].y));
+}
+template <typename R, bool INVEC>
+__global__ void __launch_bounds__(EW_THREADS) gate1_stream_kernel(typename CxT<R>::T *dst,
+                                                                 const typename CxT<R>::T *src,
+                                                                 const __grid_constant__ Gate1Args<R> g,
+                                                                 const double *norm_in, double *norm_out, void *ws) {
+    using C = typename CxT<R>::T;
+    constexpr int VE = VecOf<C>::VE, LV = VecOf<C>::LV;
+    const R s = (R)load_inv_norm(norm_in);
+    const C m00 = cx<R>(g.m[0] * s, g.m[1] * s), m01 = cx<R>(g.m[2] * s, g.m[3] * s);
+    const C m10 = cx<R>(g.m[4] * s, g.m[5] * s), m11 = cx<R>(g.m[6] * s, g.m[7] * s);
+    const uint4 *vs = reinterpret_cast<const uint4 *>(src);
+    uint4 *vd = reinterpret_cast<uint4 *>(dst);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    R part = R(0);
+    double acc[1] = {0.0};
+    auto apply = [&](C &a, C &b, uint64_t index_of_a) {          // (a, b) = the amplitudes with target bit 0 / 1
+        C r0, r1;
+        if ((index_of_a & g.ctrl) == g.ctrl) {
+            r0 = cmul(m00, a); cfma(r0, m01, b);
+            r1 = cmul(m10, a); cfma(r1, m11, b);
+        } else {
+            r0 = cx<R>(a.x * s, a.y * s); r1 = cx<R>(b.x * s, b.y * s);
+        }
+        part += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;
+        a = r0; b = r1;
+    };
+    if (INVEC) {            // complex64, target bit 0: the pair is one vector
+        const uint64_t NV = (1ull << g.n) >> LV;
+#pragma unroll 4
+        for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < NV; v += stride) {
+            C a[2];
+            unpack_vec<C>(__ldcs(vs + v), a);
+            apply(a[0], a[1], v << LV);
+            __stcs(vd + v, pack_vec(a));
+            acc[0] += (double)part; part = R(0);
+        }
+    } else {
+        const int tv = g.tbit - LV;                       // target bit in vector units
+        const uint64_t NP = ((1ull << g.n) >> LV) >> 1;   // pairs of vectors
+        const uint64_t himask = ~((1ull << tv) - 1ull);
+#pragma unroll 4
+        for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < NP; p += stride) {
+            const uint64_t v0 = p + (p & himask), v1 = v0 | (1ull << tv);
+            C a[2], b[2];
+            unpack_vec<C>(__ldcs(vs + v0), a);
+            unpack_vec<C>(__ldcs(vs + v1), b);
+#pragma unroll
+            for (int u = 0; u < VE; ++u) apply(a[u], b[u], (v0 << LV) | (uint64_t)u);
+            __stcs(vd + v0, pack_vec(a));
+            __stcs(vd + v1, pack_vec(b));
+            acc[0] += (double)part; part = R(0);
+        }
+    }
+    if (norm_out) grid_sum_publish<1>(acc, ws, norm_out);
+}
+
 // ---- partial trace (density_operator.py:127-138, np.einsum('ii...->...')) ------------------------
 // out[o] = sum_t rho[base(o) | diag(t)]: base(o) scatters the 2k bits of the output index (row / column bits of
 // the kept qubits, in the caller's order) to their flat bits in rho, diag(t) sets the row AND the column bit
@@ -853,6 +934,29 @@ int misc_outer(void *rho, const void *psi, int n, int dtype, double p, const dou
     DISPATCH_C(dtype, (outer_kernel<C><<<ew_grid(N / 8 + 1), EW_THREADS, 0, st>>>((C *)rho, (const C *)psi, n, p, norm_psi,
                                                                                  accumulate)));
     return check_launch();
+}
+
+template <typename R>
+static int gate1_launch(void *dst, const void *src, int n, const double *matrix, int tbit, uint64_t ctrl,
+                        const double *norm_in, double *norm_out, void *ws, cudaStream_t st) {
+    using C = typename CxT<R>::T;
+    Gate1Args<R> g;
+    for (int e = 0; e < 8; ++e) g.m[e] = (R)matrix[e];
+    g.ctrl = ctrl; g.n = n; g.tbit = tbit;
+    const uint64_t NV = (1ull << n) >> VecOf<C>::LV;
+    const bool invec = tbit < VecOf<C>::LV;
+    const unsigned grid = ew_grid((invec ? NV : NV / 2) / 4 + 1);
+    if (invec) gate1_stream_kernel<R, true><<<grid, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, g, norm_in, norm_out, ws);
+    else gate1_stream_kernel<R, false><<<grid, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, g, norm_in, norm_out, ws);
+    return check_launch();
+}
+
+int misc_gate1(void *dst, const void *src, int n, int dtype, const double *matrix, int tbit, uint64_t ctrl,
+               const double *norm_in, double *norm_out, void *ws, cudaStream_t st) {
+    if (n < 2 || tbit < 0 || tbit >= n) return set_error(QCS_ERR_ARG, "bad target bit");
+    if (dtype == QCS_C64) return gate1_launch<float>(dst, src, n, matrix, tbit, ctrl, norm_in, norm_out, ws, st);
+    if (dtype == QCS_C128) return gate1_launch<double>(dst, src, n, matrix, tbit, ctrl, norm_in, norm_out, ws, st);
+    return set_error(QCS_ERR_ARG, "bad dtype");
 }
 
 int misc_partial_trace(void *out, const void *rho, int d, int dtype, const int32_t *keep, int nkeep, cudaStream_t st) {

@@ -1225,6 +1225,15 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
                double *norm_out, void *ws, cudaStream_t stream) {
     if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
+    // Alternative for a pass that is one one-qubit gate: stream straight through registers with strided 128-bit
+    // loads, no shared-memory tile (qcs_misc.cu: gate1_stream_kernel).  Parity-green but measured SLOWER than the
+    // cp.async tile ring (3.07 vs 2.92 ms at 30 qubits complex64, 1.54 vs 1.48 ms at 28 qubits complex128), so
+    // it is off by default and stays selectable (QCS_STREAM1=1) as the recorded evidence for that choice.
+    if (nops == 1 && ops[0].kind == QCS_OP_DENSE && ops[0].k == 1 && n >= 12 && tune_int("QCS_STREAM1", 0) &&
+        ops[0].bitpos[0] >= 0 && ops[0].bitpos[0] < n && !(ops[0].ctrl_mask & (1ull << ops[0].bitpos[0])) &&
+        (n >= 64 || !(ops[0].ctrl_mask >> n)))
+        return misc_gate1(dst, src, n, dtype, ops[0].matrix, ops[0].bitpos[0], ops[0].ctrl_mask, norm_in, norm_out, ws,
+                          stream);
     if (nops <= 2) {
         const int rc = build_and_launch<SmallProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
         if (rc != QCS_ERR_UNSUPPORTED) return rc;
