@@ -902,7 +902,10 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     const int nreg = rb < m ? rb : m;
     bool any_dense2 = false;
     for (int i = 0; i < nops; ++i) {
-        if (hop[i].kind == 3 && (nreg < 2 || tune_int("QCS_NO_DENSE2_REG", 0))) hop[i].kind = 2;
+        // a two-target op runs in registers only if its control bits inside the tile can all stay thread bits
+        if (hop[i].kind == 3 && (nreg < 2 || tune_int("QCS_NO_DENSE2_REG", 0) ||
+                                 __builtin_popcountll(ops[i].ctrl_mask & tile_mask) > m - nreg))
+            hop[i].kind = 2;
         any_dense2 |= hop[i].kind == 3;
     }
     int pending[QCS_MAX_OPS];
@@ -1013,6 +1016,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         for (int b = m - 1; b >= 0 && S_count < nreg; --b)
             if (!((S_local | S_forbid) & (1u << b))) { S_local |= 1u << b; ++S_count; }
         if (S_count < nreg) return set_error(QCS_ERR_UNSUPPORTED, "no free tile bit left for the register set");
+        if (ntaken == 0) return set_error(QCS_ERR_UNSUPPORTED, "pass planner made no progress");   // (never loop)
         sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg; sw.thread_phase = 0; sw.has_dense2 = 0;
         int8_t reg_index_of_local[32];
         for (int j = 0; j < REG_BITS_MAX; ++j) { sw.rpos[j] = 0; sw.himask[j] = 0; sw.stride[j] = 0; }

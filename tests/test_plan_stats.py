@@ -69,3 +69,19 @@ def test_groups_the_planner_cannot_hold_are_split():
     st = (ctypes.c_int32 * 128)()
     for ops, keep, cnt in passes:
         assert _lib.load().qcs_plan_stats(n, 0, ops, len(ops), st) == 0
+
+
+def test_controlled_two_qubit_unitary_on_a_tiny_state_plans():
+    """Every tile bit of a 3-qubit state is a register bit, so the control of a controlled two-qubit unitary
+    cannot stay a thread bit: the op must fall back to the shared-memory dense op instead of stalling the
+    planner."""
+    rng = np.random.default_rng(4)
+    A = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    U, _ = np.linalg.qr(A)
+    CU = np.eye(8, dtype=np.complex128)
+    CU[4:, 4:] = U
+    for n in (3, 4, 5, 12, 20):
+        for dtype in (np.complex64, np.complex128):
+            st = _stats(n, dtype, [(CU, [n - 1, 1, 0]), (H, [0]), (CU, [0, 2, 1])])
+            assert st[2] >= 1 or st[3] >= 1          # planned: register ops and / or shared-memory dense ops
+            assert st[3] + sum(st[8 + a] for a in range(95, 107)) == 2
