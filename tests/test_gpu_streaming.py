@@ -175,3 +175,26 @@ def test_measuring_more_qubits_than_one_chunk(dtype):
     assert abs(abs(s.to_column_vector()[idx]) - 1) < 10 * tol
     np.random.seed(11)
     assert _state(vec, dtype).measure() == bits
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_controlled_two_qubit_unitaries_small_and_many_controls(dtype):
+    """The shared-memory dense op still serves two-target matrices where the register arm cannot: tiny states
+    (every tile bit is a register bit) and more than two controls."""
+    from tests.util import rand_unitary
+    rng = np.random.default_rng(14)
+    tol = TOL[np.dtype(dtype)]
+
+    def controlled(U, nc):
+        k = int(np.log2(U.shape[0]))
+        M = np.eye(2 ** (k + nc), dtype=np.complex128)
+        M[-2 ** k:, -2 ** k:] = U
+        return M
+
+    for n, nc in ((3, 1), (4, 1), (4, 2), (5, 3), (13, 3), (13, 1)):
+        vec = rand_state_vec(rng, n)
+        M = controlled(rand_unitary(rng, 2), nc)
+        qi = [int(q) for q in rng.permutation(n)[:2 + nc]]
+        got = qc.Operator.from_matrix(M)(_state(vec, dtype), qubit_indices=qi)
+        want = orc.apply_matrix_flat(M, vec, [n - 1 - q for q in qi], renorm=True)
+        assert rel_err(got.to_column_vector(), want) < tol, (n, nc, qi)
