@@ -72,7 +72,7 @@ def reference_arm(args):
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * float(np.mean([d for _, d in timed])), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'c128', 'data': 'synthetic',
-            'config': {'workload': 'layered H/RX/RZ+CNOT/CZ circuit, %d qubits, depth %d, seed %d' % (n, args.depth, SEED)},
+            'config': {'workload': 'layered H/RX/RZ+CNOT/CZ circuit, %d qubits, depth %d, seed %d, |0..0> input' % (n, args.depth, SEED)},
             'cpu_baseline': {'value': value, 'unit': 'gates/s', 'cores': 1, 'kind': 'port', 'sample': sample,
                              'host_cores': os.cpu_count()},
             'e2e': {'value': value, 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
