@@ -96,8 +96,9 @@ int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *
 
 /* Planning only, no launch and no device needed (diagnostics for the fusion scheduler and the tests):
  * how the tile engine would run this pass.  stats[0..5] = tile bits, sweeps, register ops, shared-memory
- * dense ops, tile-level predicates, scale mode; stats[8 + a] = number of register ops of arm a (the arm
- * table of csrc/gen_regops.py).  `stats` has 128 entries. */
+ * dense ops, tile-level predicates, scale mode; stats[6] = number of input ops that run in the last sweep and
+ * stats[116..127] the first 12 of their indices (-1 terminated); stats[8 + a] = number of register ops of arm
+ * a (the arm table of csrc/gen_regops.py, a < 108).  `stats` has 128 entries. */
 int qcs_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
 
 /* K5: State.probabilities (state.py:200): probs[i] = |src[i]|^2 / *norm_in ; sum to *sum_out. */

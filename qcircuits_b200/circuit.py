@@ -46,7 +46,7 @@ def tile_limits(dtype):
     return low.value, tile.value
 
 
-def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None, low_shrink=None):
+def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None, low_shrink=None, tail_trim=None):
     """Greedy fusion: repeatedly pick the tile that admits the most pending gates, where a gate may overtake
     an earlier one only if they commute (they share no bit on which either acts non-diagonally).  A tile is
     the low L flat bits plus a window of H consecutive higher bits with L + H = tile_bits; L ranges from the
@@ -58,6 +58,8 @@ def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None,
     low, tile = tile_limits(dtype)
     if low_shrink is None:
         low_shrink = int(os.environ.get('QCS_LOW_SHRINK', '6'))
+    if tail_trim is None:
+        tail_trim = int(os.environ.get('QCS_TAIL_TRIM', '8'))
     geoms = []
     if high_bits is not None:
         geoms.append((min(low, n), max(0, min(high_bits, n - min(low, n)))))
@@ -123,10 +125,30 @@ def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None,
         if not best:
             # a gate whose dense targets exceed the preferred tile even alone: libqcs shrinks the low run
             best = [remaining[0]]
+        if tail_trim > 0 and len(best) > 1:
+            best = _trim_tail_sweep(gates, best, n, dtype, tail_trim)
         passes.append(best)
         chosen = set(best)
         remaining = [i for i in remaining if i not in chosen]
     return passes
+
+
+def _trim_tail_sweep(gates, group, n, dtype, max_tail):
+    """A register sweep costs about as much as 15 register ops (the tile makes a round trip through shared
+    memory behind a barrier).  When the engine's planner needs a LAST sweep for only a few leftover ops of a
+    pass, those ops are handed back to the scheduler: they are last in the pass's execution order, so they may
+    run at the start of a later pass instead, where they usually share a sweep with other gates.
+    qcs_plan_stats (no device needed) reports the ops of the last sweep."""
+    lib = _lib.load()
+    stats = (ctypes.c_int32 * 128)()
+    ops, keep = make_ops([(gates[i].plan, gates[i].bits, False) for i in group])
+    if lib.qcs_plan_stats(n, _lib.dtype_code(dtype), ops, len(ops), stats) != 0:
+        return group
+    nsweeps, ntail = stats[1], stats[6]
+    if nsweeps < 2 or ntail < 1 or ntail > min(max_tail, 12) or ntail >= len(group):
+        return group
+    drop = {stats[116 + i] for i in range(ntail)}
+    return [g for k, g in enumerate(group) if k not in drop]
 
 
 def _cheap_form(M):

@@ -13,6 +13,8 @@
 // controlled or not, and phase multiplications on any bits) and writes them back.  The squared norm is
 // accumulated and the lazy 1/sqrt(norm) folded in while the tile streams out: each amplitude is read
 // from HBM once and written once per pass however many gates are fused.
+#include <cstdio>
+
 #include "qcs_common.cuh"
 #include "qcs_internal.h"
 
@@ -913,6 +915,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     for (int i = 0; i < nops; ++i) pending[i] = i;
     P.nsweeps = P.nregops = P.ngen = P.nouter = 0;
     P.gphase[0] = 1.0; P.gphase[1] = 0.0;
+    int last_sweep_ops[QCS_MAX_OPS], n_last_sweep = 0;     // input ops of the most recent sweep (diagnostics)
     while (npend > 0) {
         if (P.nsweeps >= Prog::MAX_SWEEPS) return set_error(QCS_ERR_UNSUPPORTED, "too many sweeps in one pass");
         Sweep &sw = P.sweeps[P.nsweeps];
@@ -1062,6 +1065,8 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             }
             return true;
         };
+        n_last_sweep = ntaken;
+        for (int t = 0; t < ntaken; ++t) last_sweep_ops[t] = taken[t];
         for (int t = 0; t < ntaken; ++t) {
             const qcs_op &o = ops[taken[t]];
             if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
@@ -1213,12 +1218,24 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     P.mat_bytes = (int32_t)(used * csize);
     // 2: complex factor, 1: real factor (lazy norm and / or deferred real scalars), 0: none
     P.scale_mode = P.gphase[1] != 0.0 ? 2 : ((norm_in || P.gphase[0] != 1.0) ? 1 : 0);
+    if (stats && tune_int("QCS_PLAN_DUMP", 0)) {      // diagnostics: the register bits and op count of every sweep
+        for (int i = 0; i < P.nsweeps; ++i) {
+            const Sweep &w = P.sweeps[i];
+            if (w.kind == SWEEP_REG)
+                std::fprintf(stderr, "sweep %d regs %d %d %d %d ops %d\n", i, w.rpos[0], w.rpos[1], w.rpos[2], w.rpos[3], w.count);
+            else std::fprintf(stderr, "sweep %d dense\n", i);
+        }
+    }
     if (stats) {       // planning only (qcs_plan_stats): tile bits, sweeps, register ops, per-arm counts
         stats[0] = m; stats[1] = P.nsweeps; stats[2] = P.nregops; stats[3] = P.ngen; stats[4] = P.nouter;
         stats[5] = P.scale_mode;
-        for (int i = 0; i < 120; ++i) stats[8 + i] = 0;
+        for (int i = 0; i < 108; ++i) stats[8 + i] = 0;
+        // the input ops that run in the last sweep (a short tail sweep is a candidate for deferral to the next
+        // pass): count in stats[6], the first 12 indices in stats[116..127], -1 terminated
+        stats[6] = n_last_sweep;
+        for (int i = 0; i < 12; ++i) stats[116 + i] = i < n_last_sweep ? last_sweep_ops[i] : -1;
         for (int i = 0; i < P.nregops; ++i)
-            if (P.regops[i].code < 120) stats[8 + P.regops[i].code]++;
+            if (P.regops[i].code < 108) stats[8 + P.regops[i].code]++;
         return QCS_OK;
     }
     const DeviceInfo &dev = device_info();
