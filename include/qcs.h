@@ -101,6 +101,16 @@ int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *
  * a (the arm table of csrc/gen_regops.py, a < 108).  `stats` has 128 entries. */
 int qcs_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
 
+/* Planning only, complex64: the tensor-core sweeps of the pass (north_star (1): "fused blocks ... run on tensor
+ * cores").  A sweep multiplies a run of gates into one dense 2^5 x 2^5 block on five tile bits (the contraction
+ * of operators.py:261 for all of them at once) and applies it with tcgen05.mma kind::tf32 as a 3-term split.
+ * stats as qcs_plan_stats, with stats[7] = sweeps with a block | (input ops inside blocks) << 8.
+ * images: 4 slots x 16384 bytes, the shared-memory operand images ("hi" tf32 image then "lo" image; K-major, no
+ * swizzle: row r, column c at byte (r%8)*16 + (r/8)*1024 + (c/4)*128 + (c%4)*4; rows 0..31 = Re U, 32..63 = Im U).
+ * info: 8 int32 per block: flat bits of block-index bits 0..4, register ops before the block, slot, sweep index.
+ * Returns QCS_ERR_UNSUPPORTED when the pass has no dense block (it then runs on the register-sweep kernel). */
+int qcs_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info);
+
 /* K5: State.probabilities (state.py:200): probs[i] = |src[i]|^2 / *norm_in ; sum to *sum_out. */
 int qcs_abs2(double *probs, const void *src, int n, int dtype, const double *norm_in,
              double *sum_out, void *ws, qcs_stream stream);

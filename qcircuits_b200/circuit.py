@@ -148,6 +148,17 @@ def _trim_tail_sweep(gates, group, n, dtype, max_tail):
     if nsweeps < 2 or ntail < 1 or ntail > min(max_tail, 12) or ntail >= len(group):
         return group
     drop = {stats[116 + i] for i in range(ntail)}
+    # Deferring an op past the rest of the pass is only legal if every kept op that follows it in program
+    # order commutes with it (same rule as the scheduler's: no shared bit on which either acts
+    # non-diagonally).  The planner's report is trusted for WHICH ops are last, never for legality.
+    for k in sorted(drop):
+        a = gates[group[k]]
+        for j in range(k + 1, len(group)):
+            if j in drop:
+                continue
+            b = gates[group[j]]
+            if (a.nd_mask & (b.nd_mask | b.d_mask)) or (a.d_mask & b.nd_mask):
+                return group
     return [g for k, g in enumerate(group) if k not in drop]
 
 

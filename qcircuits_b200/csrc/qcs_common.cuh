@@ -40,7 +40,9 @@ __device__ __forceinline__ uint32_t insert_zero32(uint32_t x, int p) {
 // ws + PROGRAM_OFFSET  : (unused, reserved)
 constexpr int WS_PARTIALS_OFFSET = 256;
 constexpr int MAX_GRID = 148 * 8;
-constexpr int64_t WS_BYTES = WS_PARTIALS_OFFSET + 2 * MAX_GRID * 8 + 1024;
+// ws + 32768          : tensor-core block-matrix images of the pass in flight, 4 slots x 16 KB (qcs_internal.h)
+constexpr int64_t WS_BYTES = 32768 + 4 * 16384;
+static_assert(WS_PARTIALS_OFFSET + 2 * MAX_GRID * 8 + 1024 <= 32768, "reduction scratch overlaps the matrix images");
 
 // Deterministic grid-wide sum of NV doubles per thread: per-CTA partials are written to the
 // workspace, the CTA that takes the last ticket adds them in a fixed order and stores the result.

@@ -53,6 +53,11 @@ struct Sweep {
     int8_t rpos[REG_BITS_MAX];       // tile-local positions of the register bits, ascending
     int16_t thread_phase;            // some PHASE op of the sweep is uniform over a thread's amplitudes
     int16_t has_dense2;              // the sweep holds a dense two-target register op (GEN2 arms)
+    // tensor-core sweeps (tile_kernel_tc): after the register ops the 2^5 x 2^5 block matrix of slot tc_slot is
+    // applied on the four register bits + one more tile bit; that bit is thread-index bit 7 of the 256-thread
+    // group and is inserted at rank `hrank` among the 8 non-register tile bits (hrank = 7: plain register sweep)
+    int16_t tc_slot;                 // -1: no tensor-core block in this sweep
+    int16_t hrank;
     // host-precomputed addressing of the compile-time-geometry path: inserting a zero at rpos[j] is
     // x += x & himask[j]; stride[j] = padded shared-memory distance in bytes between the two values of bit j
     uint32_t himask[REG_BITS_MAX];
@@ -71,6 +76,8 @@ struct TileProgram {
     const double *norm_in;
     double *norm_out;
     void *ws;
+    const void *tc_mats;             // device: n_tc block-matrix images of TC_SLOT_BYTES each (tile_kernel_tc)
+    int32_t n_tc, tc_pad;
     Sweep sweeps[NSW];
     RegOp regops[NREG];
     OuterPred outer[MAX_OUTER_PREDS];
@@ -79,6 +86,20 @@ struct TileProgram {
 };
 using SmallProg = TileProgram<4, 34, 2, 4096 + 64>;
 using LargeProg = TileProgram<72, 420, 64, 12288>;
+// passes that run on the tensor-core kernel: its shared memory also holds the block matrices, so the tables are smaller
+using TcProg = TileProgram<24, 192, 8, 6144>;
+
+// ---- tensor-core sweeps (complex64, 12-bit tiles) ------------------------------------------------
+// A sweep's dense block acts on 5 tile bits: a (2^5 x 2^5 complex) matrix applied to the 128 rows x 32 amplitudes
+// of a tile, as 3 x 12 tcgen05.mma kind::tf32 instructions (3-term split: lo*hi + hi*lo + hi*hi).
+constexpr int TC_BLOCK_BITS = 5;
+constexpr int TC_MAX_SLOTS = 4;                      // block matrices resident in shared memory per pass
+constexpr int TC_HALF_BYTES = 64 * 32 * 4;           // one image: rows 0..31 = Re U, rows 32..63 = Im U; K-major, no swizzle
+constexpr int TC_SLOT_BYTES = 2 * TC_HALF_BYTES;     // tf32 "hi" image, then the "lo" image
+constexpr int TC_GROUP_THREADS = 256;                // two groups per CTA, each streams its own tiles
+constexpr int TC_STAGES = 2;                         // ring stages per group
+constexpr int64_t WS_TC_OFFSET = 32768;              // block-matrix images live in the caller's workspace from here
+constexpr int TC_UPLOAD_RING = 8;                    // pinned host staging sets for their upload (one per launch in flight)
 static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes");
 
 struct DeviceInfo { int sms; size_t smem_per_sm; };
@@ -92,6 +113,7 @@ int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, 
                double *norm_out, void *ws, cudaStream_t stream);
 
 int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
+int tile_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info);
 
 int misc_set_basis(void *buf, int n, int dtype, uint64_t index, cudaStream_t st);
 int misc_abs2(double *probs, const void *src, int n, int dtype, const double *norm_in, double *sum_out, void *ws,

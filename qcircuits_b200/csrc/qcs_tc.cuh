@@ -1,0 +1,335 @@
+// Tensor-core sweeps of the tile engine (complex64, 12-bit tiles): tcgen05.mma kind::tf32, accumulators in
+// tensor memory.  Included by qcs_tile.cu after the register-sweep machinery.
+//
+// The contraction replaced is the same np.tensordot as everywhere (reference operators.py:261), for a run of
+// gates that the planner has multiplied into ONE dense 2^5 x 2^5 complex block U acting on five tile bits.
+//
+// Mapping.  A tile holds 2^12 amplitudes = 128 rows x 32 amplitudes, the 32 spanned by the block's five bits.
+//   A (M = 128 rows, K): the tile, in TENSOR MEMORY -- lane = row, columns = [Re a_0..a_31 | Im a_0..a_31], written
+//       by the thread that owns the row with tcgen05.st straight from the registers of the sweep (no second
+//       shared-memory image of the tile).  Two copies: tf32 "hi" = round(a), "lo" = a - hi (exact).
+//   B (N, K): the block matrix in SHARED MEMORY, K-major, no swizzle, rows 0..31 = Re U, rows 32..63 = Im U; a "hi"
+//       and a "lo" image, built on the host from the float64 product of the gates.
+//   D (M = 128, N = 64) in tensor memory: columns [Re out_0..31 | Im out_0..31], read back with tcgen05.ld by the same
+//       thread into the same registers, which then go back to the tile in shared memory.
+//   Re out = Re a . Re U^T - Im a . Im U^T ,  Im out = Re a . Im U^T + Im a . Re U^T :
+//       per split term 4 instructions M128 N64 K8 (Re a against both halves of B) + 4 M128 N32 K8 with the b-negate
+//       flag (Im a against Im U, into the Re columns) + 4 M128 N32 K8 (Im a against Re U, into the Im columns);
+//       three terms, small ones first: lo.hi + hi.lo + hi.hi.  36 instructions, ~780 cycles per tile and sweep
+//       (measured floors: 32.3 / 16.3 cycles per instruction, tools/probe/tc_probe.cu).
+// One elected lane issues the instructions after the group's barrier; completion comes back through
+// tcgen05.commit on an mbarrier.  A CTA is two groups of 256 threads that stream different tiles, so one group's
+// shared-memory and split work overlaps the other group's MMAs.
+#pragma once
+
+namespace tc {
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 consecutive columns of this thread's lane
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle; core matrix = 8 rows x 16 bytes stored contiguously,
+// LBO = bytes between the two K chunks of an instruction, SBO = bytes between 8-row groups; bit 46 = sm_100 version
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::tf32: D = f32 (bit 4), A and B = tf32 (2 at bits 7 and 10), b-negate bit 14,
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int b_neg) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_neg << 14) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// bounded wait (a lost completion traps instead of hanging the GPU)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TC_GROUP_THREADS) : "memory"); }
+
+// tensor-memory columns of one group (base = 256 * group)
+constexpr uint32_t COL_D = 0, COL_AHI_RE = 64, COL_AHI_IM = 96, COL_ALO_RE = 128, COL_ALO_IM = 160;
+constexpr uint32_t B_LBO = 128, B_SBO = 1024, B_IM_ROWS = 4 * B_SBO;     // rows 32..63 start 4 row groups in
+
+// all 36 instructions of one tile and sweep; `bimg` = shared-memory address of the slot's images (hi, then lo)
+__device__ __forceinline__ void issue_block(uint32_t tbase, uint32_t bimg) {
+    constexpr uint32_t I64 = idesc_tf32(128, 64, 0), I32 = idesc_tf32(128, 32, 0), I32N = idesc_tf32(128, 32, 1);
+    const uint64_t hi = smem_desc(bimg, B_LBO, B_SBO), lo = smem_desc(bimg + TC_HALF_BYTES, B_LBO, B_SBO);
+    constexpr uint64_t KSTEP = (2 * B_LBO) >> 4, IM = B_IM_ROWS >> 4;
+    const uint32_t d = tbase + COL_D;
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+        const uint32_t are = tbase + (term == 0 ? COL_ALO_RE : COL_AHI_RE), aim = tbase + (term == 0 ? COL_ALO_IM : COL_AHI_IM);
+        const uint64_t b = term == 1 ? lo : hi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma(d, are + 8 * ks, b + ks * KSTEP, I64, (term | ks) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma(d, aim + 8 * ks, b + IM + ks * KSTEP, I32N, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma(d + 32, aim + 8 * ks, b + ks * KSTEP, I32, 1u);
+    }
+}
+
+struct Ctx {
+    uint32_t tbase;        // tensor-memory base of this group
+    uint32_t lane_addr;    // ... with this warp's lane quarter
+    uint32_t bimg0;        // shared-memory address of block-matrix slot 0
+    uint64_t *bar;         // this group's completion barrier
+    uint32_t phase;
+    int group, gtid;
+};
+
+__device__ __forceinline__ uint32_t tf32_round(float x) {      // round to nearest (ties away): 10 explicit mantissa bits
+    return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+}
+
+// One sweep of the tensor-core kernel: register ops (the generated interpreter), then -- if the sweep has a block --
+// the dense 2^5 x 2^5 matrix on tensor cores.  Thread (rho, h) of the group owns row rho of the tile and the 16
+// amplitudes whose top block bit is h.
+template <typename Layout>
+__device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp *rops, const float2 *pool, uint64_t outer_ok,
+                                      Ctx &ctx) {
+    constexpr int NX = 16;
+    const uint32_t rho = (uint32_t)ctx.gtid & 127u, h = (uint32_t)ctx.gtid >> 7, p = (uint32_t)sw.hrank;
+    uint32_t base = ((rho >> p) << (p + 1)) | (h << p) | (rho & ((1u << p) - 1u));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) base += base & sw.himask[j];
+    const bool VEC = sw.rpos[0] == 0;
+    uint32_t addr[NX];
+    addr[0] = smem_u32(tile) + Layout::amp(base) * (uint32_t)sizeof(float2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t st = sw.stride[j];
+#pragma unroll
+        for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st;
+    }
+    float2 a[NX];
+    if (VEC) {
+#pragma unroll
+        for (int x = 0; x < NX; x += 2)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a[x].x), "=f"(a[x].y), "=f"(a[x + 1].x), "=f"(a[x + 1].y) : "r"(addr[x]) : "memory");
+    } else {
+#pragma unroll
+        for (int x = 0; x < NX; ++x)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[x].x), "=f"(a[x].y) : "r"(addr[x]) : "memory");
+    }
+    if (sw.count > 0) {
+        float2 ph = make_float2(1.0f, 0.0f);
+        if (sw.has_dense2) run_sweep_ops_dense2(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
+        else run_sweep_ops(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
+        if (sw.thread_phase) {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
+        }
+    }
+    if (sw.tc_slot >= 0) {
+        const uint32_t col = ctx.lane_addr + 16u * h;
+        {
+            uint32_t hi[NX], lo[NX];
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                hi[x] = tf32_round(a[x].x);
+                lo[x] = __float_as_uint(a[x].x - __uint_as_float(hi[x]));
+            }
+            st16(col + COL_AHI_RE, hi);
+            st16(col + COL_ALO_RE, lo);
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                hi[x] = tf32_round(a[x].y);
+                lo[x] = __float_as_uint(a[x].y - __uint_as_float(hi[x]));
+            }
+            st16(col + COL_AHI_IM, hi);
+            st16(col + COL_ALO_IM, lo);
+        }
+        wait_st();
+        fence_before();
+        group_sync(ctx.group);
+        if ((ctx.gtid >> 5) == 0) {
+            fence_after();
+            if (elect_one()) {
+                issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)sw.tc_slot * (uint32_t)TC_SLOT_BYTES);
+                commit(ctx.bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait_bounded(ctx.bar, ctx.phase);
+        ctx.phase ^= 1u;
+        fence_after();
+        {
+            uint32_t re[NX], im[NX];
+            ld16(col + COL_D, re);
+            ld16(col + COL_D + 32u, im);
+            wait_ld();
+#pragma unroll
+            for (int x = 0; x < NX; ++x) { a[x].x = __uint_as_float(re[x]); a[x].y = __uint_as_float(im[x]); }
+        }
+        fence_before();        // orders these tensor-memory reads before the next sweep's barrier + MMA
+    }
+    if (VEC) {
+#pragma unroll
+        for (int x = 0; x < NX; x += 2)
+            asm volatile("st.shared.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(a[x].x), "f"(a[x].y), "f"(a[x + 1].x), "f"(a[x + 1].y),
+                         "r"(addr[x])
+                         : "memory");
+    } else {
+#pragma unroll
+        for (int x = 0; x < NX; ++x)
+            asm volatile("st.shared.v2.f32 [%2], {%0, %1};" ::"f"(a[x].x), "f"(a[x].y), "r"(addr[x]) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// Persistent CTAs of two 256-thread groups; group g of CTA b is "virtual CTA" 2b + g of the tile loop of
+// tile_kernel_pipe (same staging, same store epilogue), with a 2-stage cp.async ring of its own.
+template <typename Prog>
+__global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const __grid_constant__ Prog P) {
+    using C = float2;
+    using Layout = PaddedLayout<C>;
+    constexpr int MT = TILE_MIN_BITS_C64, NT = TC_GROUP_THREADS, VSHIFT = 1, NK = 8, S = TC_STAGES;
+    extern __shared__ __align__(128) unsigned char smem_all[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    const int tid = threadIdx.x, g = tid >> 8, gtid = tid & (NT - 1);
+    ProgView pv;
+    const uint64_t *chunk_off;
+    const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, 2 * NT);
+    const uint64_t *hi_off = chunk_off + (1u << P.H);
+    // block-matrix images
+    unsigned char *bimg = smem_all + prog_bytes;
+    {
+        const uint4 *srcm = reinterpret_cast<const uint4 *>(P.tc_mats);
+        uint4 *dstm = reinterpret_cast<uint4 *>(bimg);
+        const uint32_t nvec = (uint32_t)P.n_tc * (TC_SLOT_BYTES / 16);
+        for (uint32_t i = tid; i < nvec; i += 2 * NT) dstm[i] = srcm[i];
+    }
+    unsigned char *ring = bimg + (size_t)P.n_tc * TC_SLOT_BYTES + (size_t)g * S * Layout::bytes(MT);
+    if (tid < 32) tc::tmem_alloc(&tmem_slot, 512);
+    if (tid == 32) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the images were written through the generic proxy
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    tc::Ctx ctx;
+    ctx.group = g; ctx.gtid = gtid; ctx.phase = 0; ctx.bar = &mma_bar[g];
+    ctx.tbase = tmem_slot + 256u * (uint32_t)g;
+    ctx.lane_addr = ctx.tbase + ((uint32_t)(((gtid >> 5) & 3) * 32) << 16);
+    ctx.bimg0 = smem_u32(bimg);
+
+    const int L = P.L;
+    const uint32_t stage_bytes = (uint32_t)Layout::bytes(MT);
+    const uint32_t svec_tid = Layout::vec((uint32_t)gtid);
+    const uint32_t svec_step = Layout::vec((uint32_t)NT);
+    const int scale_mode = P.scale_mode;
+    float fr = 1.0f, fi = 0.0f;
+    if (scale_mode) {
+        const double s = load_inv_norm(P.norm_in);
+        fr = (float)(s * P.gphase[0]); fi = (float)(s * P.gphase[1]);
+    }
+    uint64_t low_tid = 0;
+    for (int b = 0; b < MT - 3 - VSHIFT; ++b)
+        if ((gtid >> b) & 1) {
+            const int i = b + VSHIFT;
+            low_tid |= 1ull << (i < L ? i : P.hbits[i - L]);
+        }
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.src) + (low_tid >> VSHIFT);
+    uint4 *dst = reinterpret_cast<uint4 *>(P.dst) + (low_tid >> VSHIFT);
+    double nacc[1] = {0.0};
+    const uint64_t vcta = 2ull * blockIdx.x + (uint64_t)g, vgrid = 2ull * gridDim.x;
+    const uint64_t my_tiles = (P.ntiles > vcta) ? (P.ntiles - 1 - vcta) / vgrid + 1 : 0;
+    const float2 *pool = reinterpret_cast<const float2 *>(pv.pool);
+
+    auto issue_load = [&](uint64_t it, int st) {
+        const uint64_t base = tile_base_of(vcta + it * vgrid, P);
+        uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const uint4 *gp = src + ((base + hi_off[k]) >> VSHIFT);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+            sp += svec_step * 16u;
+        }
+    };
+    if (my_tiles > 0) issue_load(0, 0);
+    cp_async_commit();
+    int st = 0;
+    for (uint64_t it = 0; it < my_tiles; ++it) {
+        const uint64_t base = tile_base_of(vcta + it * vgrid, P);
+        const int parity = (int)(it & 1) + 2 * g;
+        eval_outer(pv, base, parity, gtid);
+        cp_async_wait_pending(0);          // this thread's copies of tile `it` have landed
+        tc::group_sync(g);                 // ... everyone's have, and the other stage is drained
+        if (it + 1 < my_tiles) issue_load(it + 1, st ^ 1);
+        cp_async_commit();
+        unsigned char *stage = ring + (size_t)st * stage_bytes;
+        const uint64_t outer_ok = (pv.nouter ? pv.outer_ok[parity] : 0ull) | (1ull << OUTER_SLOT_NONE);
+        for (int s = 0; s < pv.nsweeps; ++s) {
+            const Sweep &sw = pv.sweeps[s];
+            if (sw.kind == SWEEP_REG) tc::sweep<Layout>(reinterpret_cast<C *>(stage), sw, pv.regops, pool, outer_ok, ctx);
+            else apply_generic<float, Layout>(reinterpret_cast<C *>(stage), MT, pv.gen[sw.first], pool, base, gtid, NT);
+            tc::group_sync(g);
+        }
+        float tacc = 0.0f;
+        const uint4 *sbase = reinterpret_cast<const uint4 *>(stage) + svec_tid;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            uint4 val = sbase[k * svec_step];
+            if (scale_mode == 1) val = vec_scale<float>(val, fr);
+            else if (scale_mode == 2) val = vec_cscale<float>(val, fr, fi);
+            vec_norm_acc(tacc, val, 0.0f);
+            dst[(base + hi_off[k]) >> VSHIFT] = val;
+        }
+        nacc[0] += (double)tacc;
+        st ^= 1;
+    }
+    cp_async_wait_pending(0);
+    tc::fence_before();
+    __syncthreads();
+    if (tid < 32) tc::tmem_dealloc(tmem_slot, 512);
+    if (P.norm_out) grid_sum_publish<1>(nacc, P.ws, P.norm_out);
+}

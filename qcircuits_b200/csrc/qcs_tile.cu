@@ -14,6 +14,10 @@
 // accumulated and the lazy 1/sqrt(norm) folded in while the tile streams out: each amplitude is read
 // from HBM once and written once per pass however many gates are fused.
 #include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <type_traits>
 
 #include "qcs_common.cuh"
 #include "qcs_internal.h"
@@ -261,7 +265,7 @@ struct ProgView {
     const OuterPred *outer;
     const TileOp *gen;
     const void *pool;
-    uint64_t *outer_ok;     // [2]: per-tile bitmask of the outer predicates, double-buffered by tile parity
+    uint64_t *outer_ok;     // [4]: per-tile bitmask of the outer predicates, double-buffered by tile parity (x 2 groups)
     int nsweeps, nouter;
 };
 
@@ -272,7 +276,7 @@ template <typename Prog>
 static uint32_t program_smem_bytes(const Prog &P) {
     return align128(align16(P.nsweeps * (uint32_t)sizeof(Sweep)) + align16(P.nregops * (uint32_t)sizeof(RegOp)) +
                     align16(P.nouter * (uint32_t)sizeof(OuterPred)) + align16(P.ngen * (uint32_t)sizeof(TileOp)) +
-                    align16((uint32_t)P.mat_bytes) + 16u + (uint32_t)sizeof(uint64_t) * ((1u << P.H) + 8u));
+                    align16((uint32_t)P.mat_bytes) + 32u + (uint32_t)sizeof(uint64_t) * ((1u << P.H) + 8u));
 }
 
 __device__ __forceinline__ void copy_words(void *dst, const void *src, uint32_t bytes, int tid, int nt) {
@@ -301,8 +305,8 @@ __device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Pro
     pv.pool = smem + o;
     copy_words(smem + o, P.mats, (uint32_t)P.mat_bytes, tid, nt);
     o += align16((uint32_t)P.mat_bytes);
-    pv.outer_ok = reinterpret_cast<uint64_t *>(smem + o);
-    o += 16u;
+    pv.outer_ok = reinterpret_cast<uint64_t *>(smem + o);      // [2 tile parities] x [2 groups of the tensor-core kernel]
+    o += 32u;
     uint64_t *co = reinterpret_cast<uint64_t *>(smem + o);
     for (uint32_t c = tid; c < (1u << P.H); c += nt) {
         uint64_t off = 0;
@@ -697,6 +701,11 @@ __global__ void __launch_bounds__(TILE_THREADS_BULK, 1) tile_kernel_bulk(const _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variant 2: tensor-core sweeps (tcgen05 + tensor memory), complex64
+// ------------------------------------------------------------------------------------------------
+#include "qcs_tc.cuh"
+
+// ------------------------------------------------------------------------------------------------
 // host side: geometry, sweep planning, launch
 // ------------------------------------------------------------------------------------------------
 template <typename R, typename Prog>
@@ -782,6 +791,136 @@ struct HostOp {            // one entry of the caller's list, classified
 };
 }  // namespace
 
+// ---- tensor-core blocks: host side ----------------------------------------------------------------
+static thread_local unsigned char *g_block_dump = nullptr;     // set by tile_plan_blocks (diagnostics / tests)
+static thread_local int32_t *g_block_info = nullptr;
+
+static inline float tf32_round_host(float x) {          // nearest, ties away: what cvt.rna.tf32.f32 does
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+// Product of the listed ops (in order) as a 2^5 x 2^5 complex matrix over the block index, written as the two
+// shared-memory images of a slot (qcs_tc.cuh: K-major, no swizzle; rows 0..31 = Re U, rows 32..63 = Im U; "hi"
+// image = tf32(U), "lo" image = tf32(U - hi)).  block_bit(flat bit) = bit of the block index that flat bit maps to.
+template <typename F>
+static void tc_build_block(const qcs_op *ops, const int *list, int count, F block_bit, unsigned char *image) {
+    constexpr int D = 1 << TC_BLOCK_BITS;
+    static thread_local double U[D][D][2], V[D][D][2];
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c) { U[r][c][0] = r == c ? 1.0 : 0.0; U[r][c][1] = 0.0; }
+    for (int t = 0; t < count; ++t) {
+        const qcs_op &o = ops[list[t]];
+        uint32_t cmask = 0, tbit[QCS_MAX_OP_QUBITS], tmask = 0;
+        for (int b = 0; b < 64; ++b)
+            if ((o.ctrl_mask >> b) & 1ull) cmask |= 1u << block_bit(b);
+        for (int j = 0; j < o.k; ++j) { tbit[j] = 1u << block_bit(o.bitpos[j]); tmask |= tbit[j]; }
+        const int dim = 1 << o.k;
+        auto offs = [&](int x) {                       // matrix index x (operator qubit 0 = its most significant bit)
+            uint32_t off = 0;
+            for (int j = 0; j < o.k; ++j)
+                if ((x >> (o.k - 1 - j)) & 1) off |= tbit[j];
+            return off;
+        };
+        for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) { V[r][c][0] = U[r][c][0]; V[r][c][1] = U[r][c][1]; }
+        for (uint32_t sidx = 0; sidx < (uint32_t)D; ++sidx) {
+            if ((sidx & tmask) || (sidx & cmask) != cmask) continue;      // group base: targets 0, controls 1
+            for (int y = 0; y < dim; ++y) {
+                const uint32_t ry = sidx | offs(y);
+                for (int c = 0; c < D; ++c) {
+                    double ar = 0.0, ai = 0.0;
+                    if (o.kind == QCS_OP_DIAG) {
+                        const double mr = o.matrix[2 * y], mi = o.matrix[2 * y + 1];
+                        ar = mr * V[ry][c][0] - mi * V[ry][c][1];
+                        ai = mr * V[ry][c][1] + mi * V[ry][c][0];
+                    } else {
+                        for (int x = 0; x < dim; ++x) {
+                            const double mr = o.matrix[2 * (y * dim + x)], mi = o.matrix[2 * (y * dim + x) + 1];
+                            const uint32_t rx = sidx | offs(x);
+                            ar += mr * V[rx][c][0] - mi * V[rx][c][1];
+                            ai += mr * V[rx][c][1] + mi * V[rx][c][0];
+                        }
+                    }
+                    U[ry][c][0] = ar; U[ry][c][1] = ai;
+                }
+            }
+        }
+    }
+    float *hi = reinterpret_cast<float *>(image), *lo = reinterpret_cast<float *>(image + TC_HALF_BYTES);
+    for (int part = 0; part < 2; ++part)
+        for (int r = 0; r < D; ++r)
+            for (int c = 0; c < D; ++c) {
+                const int nrow = part * D + r;
+                const size_t off = ((size_t)(nrow % 8) * 16 + (size_t)(nrow / 8) * 1024 + (size_t)(c / 4) * 128 + (size_t)(c % 4) * 4) / 4;
+                const double v = U[r][c][part];
+                const float h = tf32_round_host((float)v);
+                hi[off] = h;
+                lo[off] = tf32_round_host((float)(v - (double)h));
+            }
+}
+
+// The images travel host -> device through a pinned staging ring (one set per launch in flight), so the copy is
+// asynchronous and the host buffer is not reused before its copy has run.
+static int tc_upload(const unsigned char *images, int nslots, void *ws, cudaStream_t stream) {
+    static std::mutex mu;
+    static unsigned char *pinned = nullptr;
+    static cudaEvent_t ev[TC_UPLOAD_RING];
+    static bool used[TC_UPLOAD_RING];
+    static int next = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t set_bytes = (size_t)TC_MAX_SLOTS * TC_SLOT_BYTES;
+    if (!pinned) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&pinned), set_bytes * TC_UPLOAD_RING, cudaHostAllocDefault) != cudaSuccess)
+            return set_error(QCS_ERR_CUDA, "pinned staging allocation failed");
+        for (int i = 0; i < TC_UPLOAD_RING; ++i) { cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); used[i] = false; }
+    }
+    const int slot = next;
+    next = (next + 1) % TC_UPLOAD_RING;
+    if (used[slot]) cudaEventSynchronize(ev[slot]);
+    unsigned char *stage = pinned + (size_t)slot * set_bytes;
+    std::memcpy(stage, images, (size_t)nslots * TC_SLOT_BYTES);
+    if (cudaMemcpyAsync(reinterpret_cast<unsigned char *>(ws) + WS_TC_OFFSET, stage, (size_t)nslots * TC_SLOT_BYTES,
+                        cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return set_error(QCS_ERR_CUDA, "block-matrix upload failed");
+    cudaEventRecord(ev[slot], stream);
+    used[slot] = true;
+    return QCS_OK;
+}
+
+template <typename Prog>
+static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
+    using Layout = PaddedLayout<float2>;
+    auto kern = tile_kernel_tc<Prog>;
+    static bool attr_done[64] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    constexpr int SMEM_LIMIT = 227 * 1024 - 2048;      // opt-in maximum minus the kernel's static shared memory
+    if (device < 64 && !attr_done[device]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
+            return set_error(QCS_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+        attr_done[device] = true;
+    }
+    const size_t smem = program_smem_bytes(P) + (size_t)P.n_tc * TC_SLOT_BYTES + 2 * TC_STAGES * Layout::bytes(TILE_MIN_BITS_C64);
+    if (smem > (size_t)SMEM_LIMIT) return set_error(QCS_ERR_UNSUPPORTED, "tensor-core pass does not fit shared memory");
+    P.stages = TC_STAGES;
+    uint64_t grid = (uint64_t)dev.sms;
+    if (grid * 2 > P.ntiles) grid = (P.ntiles + 1) / 2;
+    kern<<<(unsigned)grid, 2 * TC_GROUP_THREADS, smem, stream>>>(P);
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        static thread_local char msg[160];
+        std::snprintf(msg, sizeof msg, "tensor-core tile kernel launch failed: %s (grid %u, smem %zu)", cudaGetErrorString(err),
+                      (unsigned)grid, smem);
+        return set_error(QCS_ERR_CUDA, msg);
+    }
+    return QCS_OK;
+}
+
 template <typename Prog>
 static int build_and_launch(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
                             const double *norm_in, double *norm_out, void *ws, cudaStream_t stream,
@@ -859,6 +998,24 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         return r;
     };
 
+    // ---- tensor-core sweeps: which ops could join a dense block ------------------------------------------
+    constexpr bool TCPROG = std::is_same<Prog, TcProg>::value;
+    const bool use_tc = TCPROG && c64 && m == TILE_MIN_BITS_C64 && n >= TILE_MIN_BITS_C64 && tune_int("QCS_TC", 1) != 0;
+    if (TCPROG && !use_tc) return set_error(QCS_ERR_UNSUPPORTED, "not a tensor-core pass");
+    int tc_max_slots = tune_int("QCS_TC_SLOTS", TC_MAX_SLOTS);
+    if (tc_max_slots > TC_MAX_SLOTS) tc_max_slots = TC_MAX_SLOTS;
+    static thread_local unsigned char tc_images[TC_MAX_SLOTS * TC_SLOT_BYTES];
+    int tc_block_ops = 0;
+    uint32_t op_lmask[QCS_MAX_OPS];        // tile-local mask of every bit the op touches inside the tile
+    bool op_inside[QCS_MAX_OPS];           // ... and whether it touches nothing else (and fits a block)
+    for (int i = 0; i < nops; ++i) {
+        uint64_t all = ops[i].ctrl_mask;
+        for (int j = 0; j < ops[i].k; ++j) all |= 1ull << ops[i].bitpos[j];
+        op_lmask[i] = local_mask(all & tile_mask);
+        op_inside[i] = (all & ~tile_mask) == 0 && __builtin_popcountll(all) <= TC_BLOCK_BITS;
+    }
+    P.n_tc = 0; P.tc_mats = nullptr; P.tc_pad = 0;
+
     // ---- matrix pool -----------------------------------------------------------------------------------
     const size_t csize = c64 ? 8 : 16;
     const size_t pool_cap = sizeof(P.mats) / csize;
@@ -920,7 +1077,92 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         if (P.nsweeps >= Prog::MAX_SWEEPS) return set_error(QCS_ERR_UNSUPPORTED, "too many sweeps in one pass");
         Sweep &sw = P.sweeps[P.nsweeps];
         const int first = pending[0];
-        if (hop[first].kind == 2) {            // generic dense op: its own shared-memory sweep
+        sw.tc_slot = -1; sw.hrank = 7;
+        // ---- tensor-core sweep: register ops ("pre") followed by one dense block on five tile bits -------------
+        bool tc_sweep = false;
+        int blk_ops[QCS_MAX_OPS], nblk = 0, tc_hbit = -1;
+        uint32_t S_local = 0;                  // tile-local mask of the register bits
+        int S_count = 0;
+        int taken[QCS_MAX_OPS], ntaken = 0, rest[QCS_MAX_OPS], nrest = 0;
+        uint32_t S_forbid = 0;                 // control bits of the taken two-target ops: must stay thread bits
+        if (use_tc && P.n_tc < tc_max_slots) {
+            // walk the pending ops for a given block B (tile-local mask of 5 bits) whose bit `hb` is the thread bit
+            auto walk = [&](uint32_t B, int hb, int *bk, int &nbk, int *pr, int &npr, int *rs, int &nrs) -> bool {
+                const uint32_t R = B & ~(1u << hb);
+                uint64_t skip_nd = 0, skip_d = 0, mm_nd = 0, mm_d = 0;
+                nbk = npr = nrs = 0;
+                bool first_taken = false;
+                for (int i = 0; i < npend; ++i) {
+                    const int idx = pending[i];
+                    const HostOp &h = hop[idx];
+                    bool take = false;
+                    if ((h.nd_mask & (skip_nd | skip_d)) == 0 && (h.d_mask & skip_nd) == 0) {
+                        if (op_inside[idx] && (op_lmask[idx] & ~B) == 0) {
+                            bk[nbk++] = idx; mm_nd |= h.nd_mask; mm_d |= h.d_mask; take = true;
+                        } else if ((h.nd_mask & (mm_nd | mm_d)) == 0 && (h.d_mask & mm_nd) == 0) {
+                            // runs before the block: must commute with everything already in it
+                            if (h.kind == 1) take = true;
+                            else if (h.kind == 0 && ((R >> local_of(ops[idx].bitpos[0])) & 1u)) take = true;
+                            if (take) pr[npr++] = idx;
+                        }
+                    }
+                    if (take) { if (i == 0) first_taken = true; }
+                    else { rs[nrs++] = idx; skip_nd |= h.nd_mask; skip_d |= h.d_mask; }
+                }
+                return first_taken;
+            };
+            // candidate bits: the tile bits of the first pending ops, in order of appearance
+            int W[10], nW = 0;
+            uint32_t Wmask = 0;
+            for (int i = 0; i < npend && i < 48 && nW < 9; ++i) {
+                const uint32_t lm = op_lmask[pending[i]];
+                for (int b = 0; b < m && nW < 9; ++b)
+                    if (((lm >> b) & 1u) && !((Wmask >> b) & 1u)) { W[nW++] = b; Wmask |= 1u << b; }
+            }
+            for (int b = m - 1; b >= 0 && nW < TC_BLOCK_BITS; --b)      // fewer than five wanted bits: pad
+                if (!((Wmask >> b) & 1u)) { W[nW++] = b; Wmask |= 1u << b; }
+            // the first pending op must make progress: its bits (block op) or its target (register op) are required
+            uint32_t required = 0, reg_required = 0;
+            if (op_inside[first] && __builtin_popcount(op_lmask[first]) <= TC_BLOCK_BITS) required = op_lmask[first];
+            else if (hop[first].kind == 0) { required = 1u << local_of(ops[first].bitpos[0]); reg_required = required; }
+            int best_score = -1, best_nblk = 0;
+            uint32_t best_B = 0;
+            int best_hb = -1;
+            int bk2[QCS_MAX_OPS], pr2[QCS_MAX_OPS], rs2[QCS_MAX_OPS];
+            if (hop[first].kind == 0 || hop[first].kind == 1 || required) {
+                for (uint32_t sub = 0; sub < (1u << nW); ++sub) {
+                    if (__builtin_popcount(sub) != TC_BLOCK_BITS) continue;
+                    uint32_t B = 0;
+                    for (int c = 0; c < nW; ++c)
+                        if ((sub >> c) & 1u) B |= 1u << W[c];
+                    if ((B & required) != required) continue;
+                    int hb = -1;                                  // thread bit of the block: the highest non-required one, not bit 0
+                    for (int b = m - 1; b >= 1; --b)
+                        if (((B >> b) & 1u) && !((reg_required >> b) & 1u)) { hb = b; break; }
+                    if (hb < 0) continue;
+                    int nb, np, nr;
+                    if (!walk(B, hb, bk2, nb, pr2, np, rs2, nr)) continue;
+                    const int score = nb + np;
+                    if (score > best_score || (score == best_score && nb > best_nblk)) {
+                        best_score = score; best_nblk = nb; best_B = B; best_hb = hb;
+                    }
+                }
+            }
+            if (best_score > 0 && best_nblk >= 1) {
+                // the plain register sweep the existing planner would form, for comparison (ops per unit of cost:
+                // a sweep costs about as much as 15 register ops, a block about 12)
+                int nb, np, nr;
+                walk(best_B, best_hb, bk2, nb, pr2, np, rs2, nr);
+                tc_sweep = true;
+                tc_hbit = best_hb;
+                S_local = best_B & ~(1u << best_hb); S_count = TC_BLOCK_BITS - 1;
+                nblk = nb; ntaken = np; nrest = nr;
+                for (int i = 0; i < nb; ++i) blk_ops[i] = bk2[i];
+                for (int i = 0; i < np; ++i) taken[i] = pr2[i];
+                for (int i = 0; i < nr; ++i) rest[i] = rs2[i];
+            }
+        }
+        if (!tc_sweep && hop[first].kind == 2) {            // generic dense op: its own shared-memory sweep
             const qcs_op &o = ops[first];
             if (P.ngen >= Prog::MAX_GENERIC) return set_error(QCS_ERR_UNSUPPORTED, "too many generic ops");
             TileOp &t = P.gen[P.ngen];
@@ -934,6 +1176,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             t.ctrl_outer = o.ctrl_mask & ~tile_mask;
             sw.kind = SWEEP_GENERIC; sw.first = P.ngen; sw.count = 1; sw.nreg = 0;
             ++P.ngen; ++P.nsweeps;
+            n_last_sweep = 1; last_sweep_ops[0] = first;        // this op IS the most recent sweep
             for (int i = 1; i < npend; ++i) pending[i - 1] = pending[i];
             --npend;
             continue;
@@ -941,10 +1184,6 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         // choose the ops of this register sweep.  select(fixed, ...) walks the pending ops in order: an op is taken
         // if nothing it must follow is left behind and (one-target dense op) its target is a register bit; with
         // fixed == 0 the register set grows greedily with the first distinct targets met.
-        uint32_t S_local = 0;                  // tile-local mask of the register bits
-        int S_count = 0;
-        int taken[QCS_MAX_OPS], ntaken = 0, rest[QCS_MAX_OPS], nrest = 0;
-        uint32_t S_forbid = 0;                 // control bits of the taken two-target ops: must stay thread bits
         auto select = [&](uint32_t fixed, uint32_t &S_out, int &S_cnt, int *tk, int &ntk, int *rs, int &nrs) -> int {
             uint64_t blk_nd = 0, blk_d = 0;
             uint32_t S = fixed, forbid = 0;
@@ -977,8 +1216,8 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             S_out = S; S_cnt = cnt; S_forbid = forbid;
             return score;
         };
-        int best_score = select(0u, S_local, S_count, taken, ntaken, rest, nrest);
-        if (nreg >= 2 && !any_dense2 && tune_int("QCS_SWEEP_SEARCH", 1)) {
+        int best_score = tc_sweep ? 0 : select(0u, S_local, S_count, taken, ntaken, rest, nrest);
+        if (!tc_sweep && nreg >= 2 && !any_dense2 && tune_int("QCS_SWEEP_SEARCH", 1)) {
             // alternatives: register sets drawn from the first distinct dense targets still pending (always with
             // the first one, so that the sweep makes progress); keep the set that absorbs the most ops
             int cand[8], ncand = 0;
@@ -1019,8 +1258,20 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         for (int b = m - 1; b >= 0 && S_count < nreg; --b)
             if (!((S_local | S_forbid) & (1u << b))) { S_local |= 1u << b; ++S_count; }
         if (S_count < nreg) return set_error(QCS_ERR_UNSUPPORTED, "no free tile bit left for the register set");
-        if (ntaken == 0) return set_error(QCS_ERR_UNSUPPORTED, "pass planner made no progress");   // (never loop)
+        if (ntaken + nblk == 0) return set_error(QCS_ERR_UNSUPPORTED, "pass planner made no progress");   // (never loop)
         sw.kind = SWEEP_REG; sw.first = P.nregops; sw.count = 0; sw.nreg = nreg; sw.thread_phase = 0; sw.has_dense2 = 0;
+        if (tc_sweep) {
+            // thread bit 7 of the group goes to tile bit tc_hbit: its rank among the 8 non-register bits
+            sw.hrank = (int16_t)(tc_hbit - __builtin_popcount(S_local & ((1u << tc_hbit) - 1u)));
+            sw.tc_slot = (int16_t)P.n_tc;
+            int idx5[32];                                          // tile-local bit -> bit of the block index
+            for (int b = 0, j = 0; b < 32; ++b) { idx5[b] = -1; if ((S_local >> b) & 1u) idx5[b] = j++; }
+            idx5[tc_hbit] = TC_BLOCK_BITS - 1;
+            tc_build_block(ops, blk_ops, nblk, [&](int flat_bit) { return idx5[local_of(flat_bit)]; },
+                           tc_images + (size_t)P.n_tc * TC_SLOT_BYTES);
+            ++P.n_tc;
+            tc_block_ops += nblk;
+        }
         int8_t reg_index_of_local[32];
         for (int j = 0; j < REG_BITS_MAX; ++j) { sw.rpos[j] = 0; sw.himask[j] = 0; sw.stride[j] = 0; }
         for (int b = 0, j = 0; b < 32; ++b) {
@@ -1065,8 +1316,9 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             }
             return true;
         };
-        n_last_sweep = ntaken;
+        n_last_sweep = ntaken + nblk;
         for (int t = 0; t < ntaken; ++t) last_sweep_ops[t] = taken[t];
+        for (int t = 0; t < nblk; ++t) last_sweep_ops[ntaken + t] = blk_ops[t];
         for (int t = 0; t < ntaken; ++t) {
             const qcs_op &o = ops[taken[t]];
             if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
@@ -1205,7 +1457,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 }
             }
         }
-        if (sw.count > 0) {                // (a run of exact identities produces no work)
+        if (sw.count > 0 || tc_sweep) {    // (a run of exact identities produces no work)
             if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
             RegOp &endop = P.regops[P.nregops++];          // terminates the interpreter loop of this sweep
             endop.code = (uint16_t)ARM_END; endop.reg_care = endop.reg_val = 0; endop.base_care = endop.base_val = 0;
@@ -1218,17 +1470,41 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     P.mat_bytes = (int32_t)(used * csize);
     // 2: complex factor, 1: real factor (lazy norm and / or deferred real scalars), 0: none
     P.scale_mode = P.gphase[1] != 0.0 ? 2 : ((norm_in || P.gphase[0] != 1.0) ? 1 : 0);
+    if (TCPROG && P.n_tc == 0) return set_error(QCS_ERR_UNSUPPORTED, "no dense block in this pass");
     if (stats && tune_int("QCS_PLAN_DUMP", 0)) {      // diagnostics: the register bits and op count of every sweep
         for (int i = 0; i < P.nsweeps; ++i) {
             const Sweep &w = P.sweeps[i];
             if (w.kind == SWEEP_REG)
-                std::fprintf(stderr, "sweep %d regs %d %d %d %d ops %d\n", i, w.rpos[0], w.rpos[1], w.rpos[2], w.rpos[3], w.count);
+                std::fprintf(stderr, "sweep %d regs %d %d %d %d ops %d block slot %d (thread-bit rank %d)\n", i, w.rpos[0], w.rpos[1],
+                             w.rpos[2], w.rpos[3], w.count, w.tc_slot, w.hrank);
             else std::fprintf(stderr, "sweep %d dense\n", i);
+        }
+    }
+    if (stats && g_block_dump) {        // qcs_plan_blocks: the images and geometry of the tensor-core sweeps
+        std::memcpy(g_block_dump, tc_images, (size_t)P.n_tc * TC_SLOT_BYTES);
+        int w = 0;
+        for (int i = 0; i < P.nsweeps; ++i) {
+            const Sweep &sp = P.sweeps[i];
+            if (sp.kind != SWEEP_REG || sp.tc_slot < 0) continue;
+            int32_t *o = g_block_info + 8 * (w++);
+            auto flat_of = [&](int lb) { return lb < P.L ? lb : P.hbits[lb - P.L]; };
+            for (int j = 0; j < 4; ++j) o[j] = flat_of(sp.rpos[j]);
+            // the thread bit: the tile bit of rank hrank among the non-register bits
+            int rank = 0, hb = -1;
+            for (int b = 0; b < m; ++b) {
+                bool isreg = false;
+                for (int j = 0; j < 4; ++j) isreg |= sp.rpos[j] == b;
+                if (isreg) continue;
+                if (rank == sp.hrank) { hb = b; break; }
+                ++rank;
+            }
+            o[4] = flat_of(hb); o[5] = sp.count; o[6] = sp.tc_slot; o[7] = i;
         }
     }
     if (stats) {       // planning only (qcs_plan_stats): tile bits, sweeps, register ops, per-arm counts
         stats[0] = m; stats[1] = P.nsweeps; stats[2] = P.nregops; stats[3] = P.ngen; stats[4] = P.nouter;
         stats[5] = P.scale_mode;
+        stats[7] = P.n_tc | (tc_block_ops << 8);       // tensor-core sweeps, input ops multiplied into their blocks
         for (int i = 0; i < 108; ++i) stats[8 + i] = 0;
         // the input ops that run in the last sweep (a short tail sweep is a candidate for deferral to the next
         // pass): count in stats[6], the first 12 indices in stats[116..127], -1 terminated
@@ -1239,6 +1515,13 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         return QCS_OK;
     }
     const DeviceInfo &dev = device_info();
+    if constexpr (TCPROG) {
+        if (!ws) return set_error(QCS_ERR_UNSUPPORTED, "tensor-core pass needs the workspace");
+        const int rc = tc_upload(tc_images, P.n_tc, ws, stream);
+        if (rc != QCS_OK) return rc;
+        P.tc_mats = reinterpret_cast<const unsigned char *>(ws) + WS_TC_OFFSET;
+        return launch_tc(P, dev, stream);
+    }
     const int mode = tile_mode();
     return c64 ? launch_tile<float, Prog>(P, dev, mode, stream) : launch_tile<double, Prog>(P, dev, mode, stream);
 }
@@ -1259,12 +1542,31 @@ int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, 
         const int rc = build_and_launch<SmallProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
         if (rc != QCS_ERR_UNSUPPORTED) return rc;
     }
+    if (dtype == QCS_C64 && ws && n >= TILE_MIN_BITS_C64 && nops >= tune_int("QCS_TC_MIN_OPS", 3)) {
+        // passes with dense blocks run on the tensor-core kernel (the planner says "unsupported" when it finds none)
+        const int rc = build_and_launch<TcProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
+        if (rc != QCS_ERR_UNSUPPORTED) return rc;
+    }
     return build_and_launch<LargeProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
 }
 
 int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats) {
     if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
+    if (dtype == QCS_C64 && n >= TILE_MIN_BITS_C64 && nops >= tune_int("QCS_TC_MIN_OPS", 3)) {
+        const int rc = build_and_launch<TcProg>(nullptr, nullptr, n, dtype, ops, nops, nullptr, nullptr, nullptr, nullptr, stats);
+        if (rc != QCS_ERR_UNSUPPORTED) return rc;
+    }
     return build_and_launch<LargeProg>(nullptr, nullptr, n, dtype, ops, nops, nullptr, nullptr, nullptr, nullptr, stats);
+}
+
+int tile_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info) {
+    if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
+    g_block_dump = reinterpret_cast<unsigned char *>(images);
+    g_block_info = info;
+    const int rc = build_and_launch<TcProg>(nullptr, nullptr, n, QCS_C64, ops, nops, nullptr, nullptr, nullptr, nullptr, stats);
+    g_block_dump = nullptr;
+    g_block_info = nullptr;
+    return rc;
 }
 
 }  // namespace qcs

@@ -100,7 +100,8 @@ def random_gate(rng):
 
 
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
-def test_every_interpreter_arm_matches_the_oracle(dtype):
+def test_every_interpreter_arm_matches_the_oracle(dtype, monkeypatch):
+    monkeypatch.setenv('QCS_TC', '0')      # the register planner; tensor-core sweeps: tests/test_gpu_tc.py
     rng = np.random.default_rng(4242)
     n = 14
     lib = _lib.load()

@@ -2,6 +2,7 @@
 import ctypes
 
 import numpy as np
+import pytest
 
 import qcircuits_b200  # noqa: F401  (package import must work without a GPU)
 from qcircuits_b200 import _gates, _lib
@@ -11,6 +12,13 @@ H = np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2)
 X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
 CNOT = np.eye(4, dtype=np.complex128)[[0, 1, 3, 2]]
 CZ = np.diag([1, 1, 1, -1]).astype(np.complex128)
+
+
+@pytest.fixture(autouse=True)
+def register_sweeps_only(monkeypatch):
+    """These tests pin the REGISTER planner (the interpreter's arm choice); complex64 passes with dense blocks
+    otherwise go to the tensor-core planner, which tests/test_tc_plan.py covers."""
+    monkeypatch.setenv('QCS_TC', '0')
 
 
 def _stats(n, dtype, gates):
