@@ -120,9 +120,9 @@ struct Ctx {
     int group, gtid;
 };
 
-__device__ __forceinline__ uint32_t tf32_round(float x) {      // round to nearest (ties away): 10 explicit mantissa bits
-    return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-}
+// tf32 "hi" part: the 19 bits the tensor core reads (it ignores the low 13 mantissa bits); lo = x - hi is exact and
+// at most 2^-10 |x|, and ITS truncation to tf32 leaves 2^-20 |x| -- one AND + one subtraction per real number
+__device__ __forceinline__ uint32_t tf32_round(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 
 // One sweep of the tensor-core kernel: register ops (the generated interpreter), then -- if the sweep has a block --
 // the dense 2^5 x 2^5 matrix on tensor cores.  Thread (rho, h) of the group owns row rho of the tile and the 16
@@ -187,15 +187,18 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
         fence_before();
         group_sync(ctx.group);
         if ((ctx.gtid >> 5) == 0) {
+            // only this warp watches the completion barrier; the other seven sleep in the group barrier below
+            // (a spinning try_wait loop in every warp took issue slots from the other group's register work)
             fence_after();
             if (elect_one()) {
                 issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)sw.tc_slot * (uint32_t)TC_SLOT_BYTES);
                 commit(ctx.bar);
             }
             __syncwarp();
+            mbar_wait_bounded(ctx.bar, ctx.phase);
         }
-        mbar_wait_bounded(ctx.bar, ctx.phase);
         ctx.phase ^= 1u;
+        group_sync(ctx.group);
         fence_after();
         {
             uint32_t re[NX], im[NX];
