@@ -11,11 +11,10 @@ whole circuit.  Lines printed (one JSON object on stdout, rank 0 only):
              circuit, normalised state -> pinned host, all inside the timed region
   roofline   achieved HBM GB/s of the dominant kernel (tile pass): algorithmic bytes of one pass
              (2 * 2^n * sizeof(amp)) / mean launch duration, against MEASURED_PEAKS.json
-  cpu_baseline   the NumPy port of the reference algorithm (oracle/, kind "port") on the host cores,
-             bounded sample, scaled to the workload size
+  cpu_baseline   the UNMODIFIED reference (oracle/_ref, kind "reference"; copied by oracle/make_ref.py, it travels to
+             the GPU box) on the host cores: measured at 20/22/24/26 qubits, 2^n fit, extrapolated to the workload
 
-`--impl reference` times only that CPU port (the reference is pure Python/NumPy and cannot travel
-to the GPU box, so the oracle port stands in for it: same tensordot/transposes/renormalise passes).
+`--impl reference` times only that reference CPU path, same metric and config.
 """
 import argparse
 import json
@@ -36,45 +35,105 @@ SEED = 1234
 from qcircuits_b200.benchutil import ClockSampler, measured_peak, recorded_traffic  # noqa: E402
 
 
-def cpu_port_gates_per_s(orc, n_sample, n_target, budget_s, depth):
-    """Time the oracle's reference-route gate application (tensordot + copy + renormalise) on the
-    host: the first gates of the same circuit at n_sample qubits, scaled by 2^(n_sample - n_target)."""
-    gates = orc.layered_circuit(n_sample, depth, seed=SEED)
-    psi = orc.zeros_state(n_sample)
-    psi = orc.apply_operator(orc.gate_tensor(*gates[0][:2]), psi, list(gates[0][2]))   # first touch, untimed
-    done, t0 = 0, time.perf_counter()
-    for name, theta, qs in gates[1:]:
-        psi = orc.apply_operator(orc.gate_tensor(name, theta), psi, list(qs))
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    rate_sample = done / dt
-    return rate_sample * 2.0 ** (n_sample - n_target), rate_sample, done, dt
+def _cpu_engine():
+    """(kind, run_gates): the reference's own CPU implementation of the path.  kind "reference" = the UNMODIFIED
+    reference vendored as oracle/_ref by oracle/make_ref.py (it travels to the GPU box with the snapshot); kind "port" =
+    the oracle's restatement of the same route (tensordot + copy + 4-pass renormalise), only when oracle/_ref is absent.
+    run_gates(n, gates, budget_s) applies the gate list to |0..0> until the budget is spent (the first gate -- first
+    touch of the arrays -- is excluded) and returns (gates timed, seconds)."""
+    from oracle import make_ref
+    ref = make_ref.load_reference()
+    if ref is not None:
+        mk = {'H': lambda t: ref.Hadamard(), 'RX': ref.RotationX, 'RZ': ref.RotationZ, 'CNOT': lambda t: ref.CNOT(),
+              'CZ': lambda t: ref.ControlledU(ref.PauliZ())}
+
+        def run_gates(n, gates, budget_s):
+            state = ref.zeros(n)
+            state = mk[gates[0][0]](gates[0][1])(state, qubit_indices=list(gates[0][2]))
+            done, t0 = 0, time.perf_counter()
+            for name, theta, qs in gates[1:]:
+                state = mk[name](theta)(state, qubit_indices=list(qs))
+                done += 1
+                if time.perf_counter() - t0 > budget_s:
+                    break
+            return done, time.perf_counter() - t0
+        return 'reference', run_gates
+    from oracle import qc_oracle as orc
+
+    def run_gates(n, gates, budget_s):
+        psi = orc.zeros_state(n)
+        psi = orc.apply_operator(orc.gate_tensor(*gates[0][:2]), psi, list(gates[0][2]))
+        done, t0 = 0, time.perf_counter()
+        for name, theta, qs in gates[1:]:
+            psi = orc.apply_operator(orc.gate_tensor(name, theta), psi, list(qs))
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        return done, time.perf_counter() - t0
+    return 'port', run_gates
+
+
+def _blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get('num_threads', 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
+def cpu_reference_rate(n_target, depth, budget_s, sizes=None):
+    """gates/s of the reference CPU path on the layered circuit: MEASURED at several sizes that fit the time budget
+    (whole layers of the n-qubit instance of the same generator), a 2^(slope * n) fit through them, and the
+    EXTRAPOLATION to n_target when that size cannot be run (30 qubits complex128 needs 4 x 16 GiB and ~40 s per gate).
+    Returns a cpu_baseline record."""
+    from qcircuits_b200.workloads import layered_gate_list
+    kind, run_gates = _cpu_engine()
+    sizes = sizes or [s for s in (20, 22, 24, 26) if s <= n_target]
+    share = budget_s / max(1, len(sizes))
+    points = []
+    for n in sizes:
+        gates = layered_gate_list(n, depth, seed=SEED)
+        done, dt = run_gates(n, gates, share)
+        points.append({'qubits': n, 'gates_timed': done, 'seconds': dt, 'gates_per_s': done / dt})
+    xs = np.array([p['qubits'] for p in points], dtype=float)
+    ys = np.log2([p['gates_per_s'] for p in points])
+    slope = float(np.polyfit(xs, ys, 1)[0]) if len(points) > 1 else -1.0
+    last = points[-1]
+    measured_at_target = last['qubits'] == n_target
+    value = last['gates_per_s'] * 2.0 ** (slope * (n_target - last['qubits']))
+    return {'value': value, 'unit': 'gates/s', 'cores': 1, 'kind': kind, 'host_cores': os.cpu_count(),
+            'blas_threads': _blas_threads(), 'extrapolated': not measured_at_target,
+            'fit': {'log2_gates_per_s_per_qubit': slope, 'points': points},
+            'sample': ('%s path, complex128 (the reference has no complex64), whole gates of the %d-layer circuit at %s '
+                       'qubits for %.0f s each, first-touch gate excluded; %s to %d qubits with the fitted slope %.2f '
+                       'bits/qubit; the path is effectively single-threaded (cores = 1)'
+                       % ('unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port of the reference route',
+                          depth, '/'.join(str(p['qubits']) for p in points), share,
+                          'measured at' if measured_at_target else 'extrapolated', n_target, slope))}
 
 
 def reference_arm(args):
-    from oracle import qc_oracle as orc
+    """`bench.py --impl reference`: the reference's own CPU implementation of the path on the box's host cores, same
+    metric / config as the CUDA arm; every step is a bounded sample (see cpu_reference_rate)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n = args.qubits
-    n_sample = min(args.cpu_qubits, n)
     per_step = []
+    rec = None
     for _ in range(args.warmup + args.steps):
-        scaled, raw, done, dt = cpu_port_gates_per_s(orc, n_sample, n, args.cpu_budget, args.depth)
-        per_step.append((scaled, dt))
+        t0 = time.perf_counter()
+        rec = cpu_reference_rate(n, args.depth, args.cpu_budget)
+        per_step.append((rec['value'], time.perf_counter() - t0))
     timed = per_step[args.warmup:]
     value = float(np.mean([v for v, _ in timed]))
-    sample = ('first gates of the same layered circuit at %d qubits complex128 (the reference has no complex64), '
-              '%.0f s per step, gates/s scaled by 2^(%d-%d) to the %d-qubit workload' % (n_sample, args.cpu_budget, n_sample, n, n))
+    rec = dict(rec, value=value)
     line = {'impl': 'reference', 'metric': 'gates/s, random layered circuit', 'value': value, 'unit': 'gates/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * float(np.mean([d for _, d in timed])), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'c128', 'data': 'synthetic',
             'config': {'workload': 'layered H/RX/RZ+CNOT/CZ circuit, %d qubits, depth %d, seed %d, |0..0> input' % (n, args.depth, SEED)},
-            'cpu_baseline': {'value': value, 'unit': 'gates/s', 'cores': 1, 'kind': 'port', 'sample': sample,
-                             'host_cores': os.cpu_count()},
+            'cpu_baseline': rec,
             'e2e': {'value': value, 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -90,8 +149,7 @@ def main():
     ap.add_argument('--dtype', default='c64', choices=['c64', 'c128'])
     ap.add_argument('--max-ops', type=int, default=128)
     ap.add_argument('--no-fuse', action='store_true')
-    ap.add_argument('--cpu-qubits', type=int, default=24)
-    ap.add_argument('--cpu-budget', type=float, default=12.0)
+    ap.add_argument('--cpu-budget', type=float, default=24.0, help='seconds of CPU work per reference sample')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--workload', default='layered', choices=['layered', 'qpe'],
@@ -203,13 +261,8 @@ def main():
         del host_in, host_out
 
     cpu = None
-    if not args.skip_cpu:
-        from oracle import qc_oracle as orc      # the cpu_baseline leg: the only use of oracle/ here
-        n_sample = min(args.cpu_qubits, n)
-        scaled, raw, done, dt = cpu_port_gates_per_s(orc, n_sample, n, args.cpu_budget, depth)
-        cpu = {'value': scaled, 'unit': 'gates/s', 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
-               'sample': '%d gates of the same circuit at %d qubits complex128 in %.1f s (%.3f gates/s), scaled by '
-                         '2^(%d-%d)' % (done, n_sample, dt, raw, n_sample, n)}
+    if not args.skip_cpu:        # the cpu_baseline leg: the only use of oracle/ here
+        cpu = cpu_reference_rate(n, depth, args.cpu_budget)
 
     line = {
         'metric': 'gates/s, random layered circuit', 'value': value, 'unit': 'gates/s', 'n_gpus': 1,

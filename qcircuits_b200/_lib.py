@@ -120,14 +120,16 @@ def stream_ptr():
 
 
 def workspace():
-    """Per-device zero-initialised scratch: reduction tickets/partials + marginal histograms."""
+    """Zero-initialised scratch of the CURRENT stream of the current device: reduction tickets/partials, marginal
+    histograms, the block-matrix images of the pass in flight.  Calls that share a workspace must be stream-ordered
+    (include/qcs.h), so every (device, stream) pair gets its own."""
     t = require_cuda()
-    dev = t.cuda.current_device()
-    ws = _workspaces.get(dev)
+    key = (t.cuda.current_device(), stream_ptr())
+    ws = _workspaces.get(key)
     if ws is None:
         nbytes = int(load().qcs_workspace_bytes()) + MARGINAL_WS_BYTES
         ws = t.zeros(nbytes, dtype=t.uint8, device='cuda')
-        _workspaces[dev] = ws
+        _workspaces[key] = ws
     return ws
 
 

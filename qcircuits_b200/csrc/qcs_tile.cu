@@ -715,10 +715,12 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
     const size_t prog = program_smem_bytes(P);
     if (mode == TILE_MODE_BULK && (sizeof(C) << P.L) >= 16) {
         auto kern = tile_kernel_bulk<R, Prog>;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[64] = {};         // the opt-in is per device
+        int device = 0;
+        cudaGetDevice(&device);
+        if (device >= 64 || !attr_done[device]) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BUDGET);
-            attr_done = true;
+            if (device < 64) attr_done[device] = true;
         }
         const size_t tile_bytes = sizeof(C) << m;
         int S = (int)((TILE_SMEM_BUDGET - prog - 1024) / tile_bytes);
@@ -748,14 +750,16 @@ static int launch_tile(Prog &P, const DeviceInfo &dev, int mode, cudaStream_t st
         else if (fast13) { kern = tile_kernel_pipe<R, Prog, MSTD + 1, 1>; ctas = 1; }
         else if (fast11) { kern = tile_kernel_pipe<R, Prog, MSTD - 1, 4>; ctas = tune_int("QCS_PIPE_CTAS11", 4) == 3 ? 3 : 4; }
         const bool is_fast = fast12 || fast13 || fast11;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[64] = {};         // the opt-in is per device
+        int device = 0;
+        cudaGetDevice(&device);
+        if (device >= 64 || !attr_done[device]) {
             const int lim = (int)TILE_SMEM_BUDGET;
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD + 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
             cudaFuncSetAttribute(tile_kernel_pipe<R, Prog, MSTD - 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-            attr_done = true;
+            if (device < 64) attr_done[device] = true;
         }
         const size_t stage_bytes = PaddedLayout<C>::bytes(m);
         const size_t sm_smem = 227 * 1024;      // opt-in shared memory per SM; each resident CTA reserves 1 KB
@@ -900,10 +904,10 @@ static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
     int device = 0;
     cudaGetDevice(&device);
     constexpr int SMEM_LIMIT = 227 * 1024 - 2048;      // opt-in maximum minus the kernel's static shared memory
-    if (device < 64 && !attr_done[device]) {
+    if (device >= 64 || !attr_done[device]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
             return set_error(QCS_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
-        attr_done[device] = true;
+        if (device < 64) attr_done[device] = true;
     }
     const size_t smem = program_smem_bytes(P) + (size_t)P.n_tc * TC_SLOT_BYTES + 2 * TC_STAGES * Layout::bytes(TILE_MIN_BITS_C64);
     if (smem > (size_t)SMEM_LIMIT) return set_error(QCS_ERR_UNSUPPORTED, "tensor-core pass does not fit shared memory");

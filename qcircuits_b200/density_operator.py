@@ -118,6 +118,9 @@ class DensityOperator(OperatorBase):
         for i, (p, s) in enumerate(zip(ps, states)):
             if s.rank != d:
                 raise ValueError('Pure state dimensionalities do not match.')
+            if s.dtype != dtype:
+                # (the dtype= extension: a float2 buffer must never be read as double2)
+                raise TypeError('states of an ensemble must share one amplitude dtype (%s vs %s)' % (s.dtype, dtype))
             norm = s._dv.norm
             _lib.check(lib.qcs_outer_accumulate(rho.buf.data_ptr(), s._dv.buf.data_ptr(), d, rho.code, float(p),
                                                 None if norm is None else norm.data_ptr(), 1 if i else 0,

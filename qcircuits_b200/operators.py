@@ -121,6 +121,17 @@ class Operator(OperatorBase):
 
     def __init__(self, tensor):
         super().__init__(tensor)
+
+    # ``_t`` is a property so that everything derived from the tensor -- the structure analysis of the matrix and
+    # its device copies -- is dropped whenever the tensor changes: permute_qubits / swap_qubits rewrite it in place
+    # (reference operators.py:125-170) and it may be assigned directly; the reference recomputes from _t on every call.
+    @property
+    def _t(self):
+        return self._tensor
+
+    @_t.setter
+    def _t(self, value):
+        self._tensor = value
         self._plan_cache = None       # structure analysis of the matrix (diagonal / controlled)
         self._dev_matrix = {}         # dtype -> device copy, for operators wider than 4 qubits
 

@@ -2,6 +2,7 @@
 gates past each other when that is exact, and every pass fits one tile."""
 import numpy as np
 import pytest
+import pytest
 
 import qcircuits_b200 as qc
 from oracle import qc_oracle as orc
@@ -114,3 +115,44 @@ def test_swap_expansion_preserves_the_unitary():
     for g in ex:
         got = orc.apply_matrix_flat(g.plan.full, got, g.bits, renorm=False)
     assert np.max(np.abs(got - want)) < 1e-14
+
+
+def _replay(c, dtype, **kw):
+    """the scheduled order of the circuit's gates, replayed through the oracle"""
+    from qcircuits_b200.circuit import schedule_passes
+    rng = np.random.default_rng(1)
+    vec = rand_state_vec(rng, c.n)
+    want, got = vec, vec
+    for g in c.gates:
+        want = orc.apply_matrix_flat(g.plan.full, want, g.bits, renorm=False)
+    passes = schedule_passes(c.gates, c.n, dtype, **kw)
+    assert sorted(i for p in passes for i in p) == list(range(len(c.gates)))
+    for p in passes:
+        for i in p:
+            got = orc.apply_matrix_flat(c.gates[i].plan.full, got, c.gates[i].bits, renorm=False)
+    return float(np.max(np.abs(got - want)))
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+@pytest.mark.parametrize('tc', ['0', '1'])
+def test_tail_trimming_never_reorders_non_commuting_gates(dtype, tc, monkeypatch):
+    """A pass that ENDS in a dense op (3-qubit unitary, U_f) used to report the previous register sweep as its
+    tail; the trimmed gates then ran after the dense gate.  Scheduled order must equal program order up to
+    commuting gates, for every tail_trim."""
+    monkeypatch.setenv('QCS_TC', tc)
+    rng = np.random.default_rng(21)
+    for trial in range(6):
+        n = 12
+        c = Circuit(n)
+        c.append(qc.Hadamard(), [0])
+        c.append(qc.RotationX(0.3), [1])
+        if trial % 2:
+            c.append(qc.U_f(lambda a, b: a ^ b, 3), [0, 1, 2])
+        else:
+            c.append(qc.Operator.from_matrix(rand_unitary(rng, 3)), [0, 1, 2])
+        for _ in range(trial):
+            c.append(qc.Hadamard(), [int(rng.integers(n))])
+            c.append(qc.CNOT(), [int(q) for q in rng.permutation(n)[:2]])
+            c.append(qc.Operator.from_matrix(rand_unitary(rng, 3)), [int(q) for q in rng.permutation(n)[:3]])
+        for tail_trim in (0, 4, 8, 12):
+            assert _replay(c, dtype, tail_trim=tail_trim) < 1e-12, (trial, tail_trim)

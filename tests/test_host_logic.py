@@ -228,3 +228,29 @@ def test_chunked_sampling_equals_the_flat_inverse_cdf():
     got = _sample_chunked(lambda db, do, cb: np.full(2 ** len(cb), 1.0 / 2 ** len(cb)), list(range(6)), None, 3)
     assert got == int(expect_u * 64)
     assert np.random.random_sample() == after
+
+
+def test_operator_caches_follow_the_tensor():
+    """permute_qubits / swap_qubits rewrite Operator._t in place (reference operators.py:125-170); the cached structure
+    analysis and device matrices must not survive that (the reference recomputes from _t on every call)."""
+    from qcircuits_b200 import _gates
+    op = qc.CNOT()
+    before = op._plan()
+    assert before.controls == [0] and before.targets == [1]
+    op.swap_qubits(0, 1)
+    after = op._plan()
+    assert after is not before and after.controls == [1] and after.targets == [0]
+    want = _gates.analyze(op.to_matrix())
+    assert after.controls == want.controls and after.targets == want.targets
+    tof = qc.Toffoli()
+    tof._plan()
+    tof.permute_qubits([2, 0, 1])
+    assert sorted(tof._plan().controls) == sorted(_gates.analyze(tof.to_matrix()).controls)
+    assert tof._plan().targets == _gates.analyze(tof.to_matrix()).targets
+    h = qc.Hadamard()
+    h._plan()
+    h._t = qc.PauliX()._t            # direct assignment
+    assert np.array_equal(h._plan().full, qc.PauliX().to_matrix())
+    import copy
+    c = copy.deepcopy(tof)
+    assert np.array_equal(c._t, tof._t) and c._plan().targets == tof._plan().targets

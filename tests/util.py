@@ -25,3 +25,19 @@ def rel_err(got, want):
 
 
 TOL = {np.dtype(np.complex128): 1e-12, np.dtype(np.complex64): 1e-5}
+
+
+# achieved error / tolerance of every parity assertion made through check_close, reported at the end of the run
+# (tests/conftest.py) so that the log shows how far each test is from the north-star bar, not only that it passed
+ACHIEVED = {}
+
+
+def check_close(got, want, dtype, label, factor=1.0):
+    """assert rel_err(got, want) < factor * TOL[dtype] and record err / TOL.  `factor` != 1 must be justified at the
+    call site with the measured number."""
+    tol = TOL[np.dtype(dtype)]
+    err = rel_err(got, want)
+    key = '%s[%s]' % (label, np.dtype(dtype).name)
+    ACHIEVED[key] = max(ACHIEVED.get(key, 0.0), err / tol)
+    assert err < factor * tol, '%s: error %.3e = %.2f x the %.0e tolerance' % (key, err, err / tol, tol)
+    return err
