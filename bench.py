@@ -214,7 +214,7 @@ def main():
     # layers of the same circuit, unfused, timed the same way
     if qpe is not None:
         k = min(12, n - 2)
-        ps = out._measurement_probabilities(list(range(k)))
+        ps = out.marginal_probabilities(list(range(k)))
         qpe.update({'estimated_phase_%d_bits' % k: int(np.argmax(ps)) / 2.0 ** k, 'peak_probability': float(ps.max())})
     from qcircuits_b200.workloads import layered_gate_list, operator_for
     from qcircuits_b200.circuit import Circuit

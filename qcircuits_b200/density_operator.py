@@ -113,6 +113,16 @@ class DensityOperator(OperatorBase):
             raise ValueError('Probabilities should sum to 1.')
         d = states[0].rank
         dtype = states[0].dtype
+        if d == 0:
+            # rank-0 states (what is left after measuring and removing the last qubit; the reference's own tests
+            # build density operators of them, tests.py:1146-1190): the 1 x 1 "matrix" sum p |a|^2 / <a|a>, on the host
+            total = 0.0
+            for p, s in zip(ps, states):
+                if s.rank != 0:
+                    raise ValueError('Pure state dimensionalities do not match.')
+                a = complex(np.asarray(s._t).reshape(-1)[0])
+                total += float(p) * (a * np.conj(a)).real
+            return DensityOperator(np.array(total, dtype=np.complex128), dtype=dtype)
         rho = DeviceVector(_lib.alloc_amplitudes(2 * d, dtype), None, 2 * d, dtype)
         lib = _lib.load()
         for i, (p, s) in enumerate(zip(ps, states)):

@@ -226,6 +226,56 @@ class CudaEngine:
                                         _lib.workspace().data_ptr(), _lib.stream_ptr()))
         return out[:1]
 
+    # -- the drop-in State surface (measure, host transfer, tensor product) ----------------------------------------
+    def load_host(self, vec):
+        """this rank's 2^n_local amplitudes from a host array"""
+        self.buf.copy_(_lib.upload(np.asarray(vec).reshape(-1), self.dtype))
+
+    def to_host(self):
+        return _lib.download(self.buf, self.dtype).astype(np.complex128)
+
+    def zero(self):
+        self.buf.zero_()
+
+    def scale(self, factor):
+        _lib.check(_lib.load().qcs_scale(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, float(factor), 0.0,
+                                         None, None, None, _lib.stream_ptr()))
+
+    def collapse(self, bitpos, outcome, remove, scale):
+        """keep the amplitudes whose bits at bitpos equal outcome, times scale (qcs_collapse); remove drops those bits"""
+        lib = _lib.load()
+        m = len(bitpos)
+        n_out = self.n_local - m if remove else self.n_local
+        dst = _lib.alloc_amplitudes(n_out, self.dtype) if remove else self.spare
+        _lib.check(lib.qcs_collapse(dst.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, _lib.int32_array(bitpos), m,
+                                    int(outcome), 1 if remove else 0, float(scale), None, _lib.workspace().data_ptr(),
+                                    _lib.stream_ptr()))
+        if remove:
+            self.buf, self.n_local = dst, n_out
+            self.spare = _lib.alloc_amplitudes(n_out, self.dtype)
+        else:
+            self.buf, self.spare = self.spare, self.buf
+        self.launches += 1
+
+    def kron_low(self, vec):
+        """shard <- shard (x) vec: the new qubits become the lowest physical bits (qcs_kron)"""
+        vec = np.asarray(vec).reshape(-1)
+        nb = int(round(np.log2(vec.size)))
+        small = _lib.upload(vec, self.dtype)
+        dst = _lib.alloc_amplitudes(self.n_local + nb, self.dtype)
+        _lib.check(_lib.load().qcs_kron(dst.data_ptr(), self.buf.data_ptr(), self.n_local, small.data_ptr(), nb, self.code,
+                                        None, None, None, None, _lib.stream_ptr()))
+        self.n_local += nb
+        self.buf = dst
+        self.spare = _lib.alloc_amplitudes(self.n_local, self.dtype)
+
+    def clone(self):
+        other = CudaEngine.__new__(CudaEngine)
+        other.n_local, other.dtype, other.code, other.launches = self.n_local, self.dtype, self.code, 0
+        other.buf = self.buf.clone()
+        other.spare = _lib.alloc_amplitudes(self.n_local, self.dtype)
+        return other
+
     def marginals(self, bitpos):
         t = _lib.torch()
         out = t.empty(1 << len(bitpos), dtype=t.float64, device='cuda')
@@ -237,11 +287,19 @@ class CudaEngine:
 
 
 class ShardedState:
-    """This rank's part of an n-qubit state spread over ``world`` = 2^g ranks."""
+    """This rank's part of an n-qubit state spread over ``world`` = 2^g ranks (one process per GPU).
+
+    The drop-in surface of a sharded state (north_star (4): "states of 32 qubits or more sharded ... across 2/4/8
+    GPUs") mirrors qc.State where the operation makes sense at that size: ``Operator.__call__(state, qubit_indices)``
+    (operators.py:280-323), ``Circuit.run``, ``measure`` (state.py:307-387: per-rank marginal histogram -> all-reduce ->
+    the SAME host inverse-CDF draw on every rank -> local collapse; a measured rank bit zeroes whole shards),
+    marginal probabilities of chosen qubits, ``from_column_vector`` / ``to_column_vector`` (state.py:32-60,99-111) and
+    the tensor product with an ordinary State (tensors.py:56-76).  Every method is collective: all ranks call it with
+    the same arguments."""
 
     def __init__(self, n, dtype=np.complex64, rank=None, world=None, engine=None, group=None):
         import torch.distributed as dist
-        self.rank = dist.get_rank(group) if rank is None else rank
+        self.proc_rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.g = int(round(np.log2(self.world)))
         if 2 ** self.g != self.world:
@@ -257,7 +315,7 @@ class ShardedState:
     def set_zeros(self, layout=None):
         """|0...0>: index 0 lives on rank 0 under any layout."""
         self.phys = list(initial_layout(self.n, self.g) if layout is None else layout)
-        self.engine.set_basis(0 if self.rank == 0 else None)
+        self.engine.set_basis(0 if self.proc_rank == 0 else None)
         self.norm = None
         return self
 
@@ -269,7 +327,7 @@ class ShardedState:
             if step[0] == 'local':
                 rank_gates = []
                 for idx, bits in step[1]:
-                    sp = specialize(gates[idx].plan, bits, self.n_local, self.rank)
+                    sp = specialize(gates[idx].plan, bits, self.n_local, self.proc_rank)
                     if sp is not None:
                         rank_gates.append(_Gate(None, sp[1], plan=sp[0]))
                 if rank_gates:
@@ -282,6 +340,209 @@ class ShardedState:
         self.phys = phys
         self.norm = None
         return self
+
+    # -- construction / export ------------------------------------------------------------------------------------
+    @property
+    def rank(self):
+        """number of qubits (Tensor.rank of the reference, tensors.py:41-54); the process index is ``proc_rank``"""
+        return self.n
+
+    @property
+    def shape(self):
+        return (2,) * self.n
+
+    @classmethod
+    def zeros(cls, n, dtype=np.complex64, **kw):
+        return cls(n, dtype, **kw).set_zeros()
+
+    @classmethod
+    def from_column_vector(cls, vec, dtype=np.complex64, **kw):
+        """State.from_column_vector (state.py:32-60) for a sharded state: ``vec`` is the full 2^n vector; every rank
+        passes the same array and keeps its own contiguous block of 2^(n-g) amplitudes."""
+        vec = np.asarray(vec).reshape(-1)
+        n = int(round(np.log2(vec.size)))
+        if 2 ** n != vec.size:
+            raise ValueError('Vector length should be a power of 2.')
+        st = cls(n, dtype, **kw)
+        block = 2 ** st.n_local
+        st.phys = canonical_layout(st.n)
+        st.engine.load_host(vec[st.proc_rank * block:(st.proc_rank + 1) * block])
+        return st
+
+    def shards_on_host(self):
+        """every rank's block, on every rank (for states that fit a host: tests, small registers)"""
+        import torch.distributed as dist
+        shards = [None] * self.world
+        dist.all_gather_object(shards, self.engine.to_host(), group=self.group)
+        return shards
+
+    def to_column_vector(self):
+        """the whole normalised vector in the reference's order (qubit 0 = most significant bit, state.py:99-111)"""
+        n = self.n
+        if n > 28:
+            raise ValueError('to_column_vector gathers 2^n amplitudes on every host: use marginals / measure at this size')
+        full = np.concatenate(self.shards_on_host())
+        idx = np.arange(2 ** n)
+        src = np.zeros_like(idx)
+        for q in range(n):
+            src |= ((idx >> (n - 1 - q)) & 1) << self.phys[q]
+        out = full[src]
+        return out / np.sqrt(np.sum(np.abs(out) ** 2))
+
+    @property
+    def probabilities(self):
+        """|amplitude|^2 as an array of shape (2,) * n (state.py:187-203); only for states that fit a host"""
+        v = self.to_column_vector()
+        return (np.abs(v) ** 2).reshape([2] * self.n)
+
+    def copy(self):
+        other = ShardedState.__new__(ShardedState)
+        other.__dict__.update(self.__dict__)
+        other.phys = list(self.phys)
+        other.engine = self.engine.clone()
+        return other
+
+    # -- gates -------------------------------------------------------------------------------------------------------
+    def apply_(self, op, qubit_indices=None):
+        """op on the listed qubits, in place (the out-of-place form is Operator.__call__)"""
+        from .circuit import Circuit
+        c = Circuit(self.n)
+        c.append(op, qubit_indices)
+        return self.run(c)
+
+    def _apply_operator(self, op, qubit_indices):
+        """Operator.__call__(state, qubit_indices) (operators.py:280-323): a NEW state, the argument untouched"""
+        return self.copy().apply_(op, qubit_indices)
+
+    def _with_factor(self, other, other_first):
+        from .state import State
+        if not isinstance(other, State):
+            return NotImplemented
+        nb = other.rank
+        out = self.copy()
+        out.engine.kron_low(other.to_column_vector())
+        mine, theirs = [p + nb for p in self.phys], [nb - 1 - j for j in range(nb)]
+        out.phys = theirs + mine if other_first else mine + theirs
+        out.n, out.n_local = self.n + nb, self.n_local + nb
+        return out
+
+    def __mul__(self, other):
+        """tensor product with an ordinary State (tensors.py:56-76): the result's qubits are this state's, then the
+        other's; physically the new qubits take the lowest local bits of every shard (only the qubit map knows)"""
+        return self._with_factor(other, False)
+
+    def __rmul__(self, other):
+        return self._with_factor(other, True)
+
+    # -- measurement -------------------------------------------------------------------------------------------------
+    def _raw_marginals(self, qubits):
+        """unnormalised marginal sums over the listed logical qubits (first = MSB), all-reduced over the ranks"""
+        import torch.distributed as dist
+        t = _lib.torch()
+        m = len(qubits)
+        pos = [self.phys[q] for q in qubits]
+        local = [(j, p) for j, p in enumerate(pos) if p < self.n_local]
+        part = self.engine.marginals([p for _, p in local]) if local else self.engine.norm2().reshape(1)
+        full = t.zeros(1 << m, dtype=t.float64, device=part.device)
+        idx = np.zeros(1 << len(local), dtype=np.int64)
+        fixed = 0
+        for j, p in enumerate(pos):
+            if p >= self.n_local and (self.proc_rank >> (p - self.n_local)) & 1:
+                fixed |= 1 << (m - 1 - j)
+        for x in range(1 << len(local)):
+            o = fixed
+            for k, (j, _) in enumerate(local):
+                if (x >> (len(local) - 1 - k)) & 1:
+                    o |= 1 << (m - 1 - j)
+            idx[x] = o
+        full[t.from_numpy(idx).to(part.device)] = part.to(full.dtype)
+        dist.all_reduce(full, group=self.group)
+        return full.cpu().numpy()
+
+    def marginal_probabilities(self, qubit_indices):
+        """normalised marginal distribution of the listed qubits (first = most significant bit); all ranks get it"""
+        raw = self._raw_marginals([int(q) for q in qubit_indices])
+        return raw / raw.sum()
+
+    def measure(self, qubit_indices=None, remove=False, u=None):
+        """Measure the listed qubits, collapsing the state in place (state.py:307-387).  int argument -> int, else a
+        tuple; the first listed qubit is the most significant bit of the outcome.  One uniform is drawn per call --
+        from NumPy's global stream on rank 0 (like np.random.choice at state.py:364) and broadcast, or ``u``."""
+        import torch.distributed as dist
+        int_arg = False
+        if isinstance(qubit_indices, (int, np.integer)):
+            qubit_indices, int_arg = [int(qubit_indices)], True
+        if qubit_indices is None:
+            qubit_indices = range(self.n)
+        qubit_indices = [int(q) for q in qubit_indices]
+        if qubit_indices == []:
+            raise ValueError('Must measure at least one qubit.')
+        if min(qubit_indices) < 0 or max(qubit_indices) >= self.n:
+            raise ValueError('Trying to measure qubit index i not 0<=i<d, '
+                             'where d is the rank of the state vector.')
+        if len(qubit_indices) != len(set(qubit_indices)):
+            raise ValueError('Qubit indices list contains repeated elements.')
+        m = len(qubit_indices)
+        if m > 24:
+            raise ValueError('measure at most 24 qubits of a sharded state per call')
+        box = [float(np.random.random_sample()) if u is None else float(u)]
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        raw = self._raw_marginals(qubit_indices)
+        cdf = np.cumsum(raw)
+        cdf = cdf / cdf[-1]
+        outcome = min(int(np.searchsorted(cdf, box[0], side='right')), len(cdf) - 1)
+        bits = tuple((outcome >> i) & 1 for i in range(m - 1, -1, -1))
+        if remove:
+            self._make_local(qubit_indices)
+        scale = 1.0 / np.sqrt(raw[outcome])            # collapse, /sqrt(p) and the trailing renormalise in one factor
+        pos = [self.phys[q] for q in qubit_indices]
+        local = [(j, p) for j, p in enumerate(pos) if p < self.n_local]
+        alive = all(((self.proc_rank >> (p - self.n_local)) & 1) == bits[j] for j, p in enumerate(pos) if p >= self.n_local)
+        if not alive:
+            self.engine.zero()                          # this shard disagrees with a measured rank bit
+        elif local:
+            lo = 0
+            for j, _ in local:
+                lo = (lo << 1) | bits[j]
+            self.engine.collapse([p for _, p in local], lo, bool(remove), scale)
+        else:
+            self.engine.scale(scale)
+        if remove:                                      # (_make_local: every measured qubit sits on a local bit)
+            gone = sorted(pos)
+            keep = [q for q in range(self.n) if q not in set(qubit_indices)]
+            self.phys = [self.phys[q] - sum(1 for b in gone if b < self.phys[q]) for q in keep]
+            self.n -= m
+            self.n_local -= m
+        self.norm = None
+        return bits[0] if int_arg else bits
+
+    def _make_local(self, qubits):
+        """bring the listed logical qubits onto local physical bits (removal shrinks every shard alike): park them below
+        the top g local bits, then trade the rank bits for those top bits if any listed qubit sits on a rank bit"""
+        if all(self.phys[q] < self.n_local for q in qubits):
+            return
+        if len(qubits) > self.n_local - 2 * self.g:
+            raise ValueError('too many qubits to remove from a state sharded this way')
+        top = set(range(self.n_local - self.g, self.n_local))
+        qubit_at = {p: q for q, p in enumerate(self.phys)}
+        listed = set(qubits)
+        movers = [q for q in qubits if self.phys[q] in top]
+        safe = [b for b in range(self.n_local - self.g) if qubit_at[b] not in listed]
+        src_bit = list(range(self.n_local))
+        for q, b in zip(movers, safe):
+            a = self.phys[q]
+            other = qubit_at[b]
+            src_bit[a], src_bit[b] = src_bit[b], src_bit[a]
+            self.phys[q], self.phys[other] = b, a
+            qubit_at[b], qubit_at[a] = q, other
+        if movers:
+            self.engine.permute(src_bit)
+        self.engine.exchange(self.group)
+        self.exchanges += 1
+        qubit_at = {p: q for q, p in enumerate(self.phys)}
+        for i in range(self.g):
+            qa, qb = qubit_at[self.n_local + i], qubit_at[self.n_local - self.g + i]
+            self.phys[qa], self.phys[qb] = self.n_local - self.g + i, self.n_local + i
 
     def norm2(self):
         """Squared norm of the whole state (all-reduce of the per-rank sums)."""
@@ -309,7 +570,7 @@ class ShardedState:
                 if (x >> (len(local) - 1 - k)) & 1:
                     o |= 1 << (m - 1 - j)
             for j, p in enumerate(pos):
-                if p >= self.n_local and (self.rank >> (p - self.n_local)) & 1:
+                if p >= self.n_local and (self.proc_rank >> (p - self.n_local)) & 1:
                     o |= 1 << (m - 1 - j)
             idx[x] = o
         full[t.from_numpy(idx).to(part.device)] = part

@@ -205,6 +205,9 @@ class Operator(OperatorBase):
         if isinstance(arg, DensityOperator):
             qi = _validated_indices(self.rank // 2, arg.rank // 2, qubit_indices)
             return arg._apply_operator(self, qi)
+        if type(arg).__name__ == 'ShardedState':          # (dist.py is only imported by multi-GPU programs)
+            qi = _validated_indices(self.rank // 2, arg.rank, qubit_indices)
+            return arg._apply_operator(self, qi)
         return self._compose(arg, qubit_indices)
 
     def __call__(self, arg, qubit_indices=None):

@@ -10,6 +10,8 @@ for amplitude work.
 Extension over the reference (which hard-codes complex128, tensors.py:18): constructors and
 factories accept ``dtype=np.complex64``.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -107,6 +109,8 @@ class State(Tensor):
     def __mul__(self, scalar):
         if isinstance(scalar, (float, int, complex)):
             return State(self._dv.scaled(scalar))
+        if type(scalar).__name__ == 'ShardedState':        # small (x) sharded: the sharded operand builds the product
+            return scalar.__rmul__(self)
         return self.tensor_product(scalar)
 
     def __rmul__(self, scalar):
@@ -204,9 +208,21 @@ class State(Tensor):
         return State(self._dv.apply_dense(op._device_matrix(self._dv.dtype), plan.k, bits))
 
     # -- measurement -----------------------------------------------------------------------------------------
-    def _measurement_probabilities(self, qubit_indices):
+    def marginal_probabilities(self, qubit_indices):
+        """float64 marginal distribution of the listed qubits (first = most significant bit of the outcome): the
+        ``ps`` of the reference's State._measurement_probabilities (state.py:262-269), from the marginal kernel."""
         d = self.rank
-        return self._dv.marginals([d - 1 - q for q in qubit_indices])
+        return self._dv.marginals([d - 1 - int(q) for q in qubit_indices])
+
+    def _measurement_probabilities(self, qubit_indices):
+        """(ps, num_outcomes, amplitudes, permute) exactly like the reference's private helper (state.py:262-269; its
+        own tests unpack all four, tests.py:1051).  ``amplitudes`` -- the state transposed so that the measured qubits
+        lead -- is a host copy made only when somebody reads it."""
+        qubit_indices = list(qubit_indices)
+        ps = self.marginal_probabilities(qubit_indices)
+        unmeasured = list(set(range(self.rank)) - set(qubit_indices))
+        permute = qubit_indices + unmeasured
+        return ps, 2 ** len(qubit_indices), _LazyTranspose(self, permute), permute
 
     def measure(self, qubit_indices=None, remove=False, u=None):
         """Measure the listed qubits in the computational basis, collapsing this state in place
@@ -266,6 +282,28 @@ class State(Tensor):
     def reduced_density_operator(self, qubit_indices):
         """Reduced density operator of the listed qubits (state.py:285-305)."""
         return self.density_operator().reduced_density_operator(qubit_indices)
+
+
+class _LazyTranspose:
+    """np.transpose(state._t, permute), materialised on first use (a full device -> host copy)"""
+
+    def __init__(self, state, permute):
+        self._state, self._permute, self._value = state, permute, None
+
+    def _get(self):
+        if self._value is None:
+            self._value = np.transpose(self._state._t, self._permute)
+        return self._value
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self._get(), dtype=dtype)
+
+    def __getitem__(self, key):
+        return self._get()[key]
+
+    @property
+    def shape(self):
+        return (2,) * self._state.rank
 
 
 MEASURE_CHUNK_BITS = 16
@@ -334,10 +372,31 @@ def _basis(d, index, dtype):
     return State(DeviceVector.basis(d, index, dtype))
 
 
-def zeros(d=1, dtype=np.complex128):
-    """|0...0> on d qubits: a device memset plus one store."""
+SHARD_MIN_QUBITS = int(os.environ.get('QCS_SHARD_MIN_QUBITS', '32'))
+
+
+def _wants_sharding(d, sharded):
+    """north_star (4): states of 32 qubits or more are sharded over the ranks of the process group (one process per
+    GPU, torchrun); ``sharded=True / False`` overrides, QCS_SHARD_MIN_QUBITS moves the threshold."""
+    if sharded is not None:
+        return bool(sharded)
+    if d < SHARD_MIN_QUBITS:
+        return False
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False
+
+
+def zeros(d=1, dtype=np.complex128, sharded=None):
+    """|0...0> on d qubits: a device memset plus one store.  In a multi-GPU program (torch.distributed initialised,
+    one process per GPU) a state of >= 32 qubits comes back as a dist.ShardedState."""
     if d < 1:
         raise ValueError('Rank must be at least 1.')
+    if _wants_sharding(d, sharded):
+        from .dist import ShardedState
+        return ShardedState.zeros(d, dtype)
     return _basis(d, 0, dtype)
 
 

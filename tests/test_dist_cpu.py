@@ -62,6 +62,49 @@ class NumpyEngine:
     def norm2(self):
         return torch.tensor([float(np.sum(np.abs(self.vec) ** 2))], dtype=torch.float64)
 
+    # the drop-in State surface (same contract as dist.CudaEngine)
+    def load_host(self, vec):
+        self.vec = np.array(vec, dtype=np.complex128).reshape(-1)
+
+    def to_host(self):
+        return self.vec.copy()
+
+    def zero(self):
+        self.vec[:] = 0
+
+    def scale(self, factor):
+        self.vec = self.vec * factor
+
+    def collapse(self, bitpos, outcome, remove, scale):
+        n, m = self.n_local, len(bitpos)
+        idx = np.arange(2 ** n)
+        x = np.zeros_like(idx)
+        for p in bitpos:
+            x = (x << 1) | ((idx >> p) & 1)
+        keep = x == outcome
+        if remove:
+            rest = [b for b in range(n) if b not in set(bitpos)]
+            sel = idx[keep]
+            dst = np.zeros_like(sel)
+            for j, b in enumerate(rest):
+                dst |= ((sel >> b) & 1) << j
+            out = np.zeros(2 ** (n - m), dtype=np.complex128)
+            out[dst] = self.vec[sel] * scale
+            self.vec, self.n_local = out, n - m
+        else:
+            self.vec = np.where(keep, self.vec * scale, 0)
+        self.launches += 1
+
+    def kron_low(self, vec):
+        vec = np.asarray(vec).reshape(-1)
+        self.vec = np.kron(self.vec, vec)
+        self.n_local += int(round(np.log2(vec.size)))
+
+    def clone(self):
+        other = NumpyEngine(self.n_local, self.group)
+        other.vec = self.vec.copy()
+        return other
+
     def marginals(self, bitpos):
         n = self.n_local
         idx = np.arange(2 ** n)
@@ -199,3 +242,93 @@ def test_headline_sharded_schedule_is_mostly_local():
     assert sorted(phys) == list(range(n))
     assert swaps <= 40
     print('exchanges for 36q depth 40 over 8 ranks:', swaps)
+
+
+def _dropin_worker(rank, world, port, n, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = int(np.log2(world))
+        rng = np.random.default_rng(77)
+        vec = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        vec /= np.linalg.norm(vec)
+        results = {}
+        st = qd.ShardedState.from_column_vector(vec, np.complex128, engine=NumpyEngine(n - g))
+        assert st.rank == n and st.shape == (2,) * n
+        results['roundtrip'] = st.to_column_vector()
+        # Operator.__call__ leaves its argument alone and returns a new sharded state
+        U = rand_unitary(np.random.default_rng(5), 2)
+        st2 = qc.Operator.from_matrix(U)(st, qubit_indices=[0, n - 2])
+        results['applied'] = st2.to_column_vector()
+        results['untouched'] = st.to_column_vector()
+        results['marg'] = st2.marginal_probabilities([n - 1, 0, 3])
+        # measurement: same uniform on every rank; rank-bit and local qubits, keep and remove
+        cases = []
+        for qs, remove, u in (([0, 3], False, 0.37), ([n - 1], False, 0.81), ([0], True, 0.05), ([2, 0, n - 1], True, 0.66),
+                              (None, False, 0.5)):
+            s3 = st2.copy()
+            bits = s3.measure(qs, remove=remove, u=u)
+            cases.append((qs, remove, u, bits, s3.to_column_vector(), s3.rank))
+        results['measure'] = cases
+        # int argument -> int result; the global NumPy stream on rank 0 supplies the uniform when u is None
+        np.random.seed(123)
+        s4 = st2.copy()
+        b = s4.measure(1)
+        results['int_result'] = (b, s4.to_column_vector())
+        # tensor products with an ordinary (small) state on either side
+        phi = rng.normal(size=4) + 1j * rng.normal(size=4)
+        phi /= np.linalg.norm(phi)
+
+        results['phi'] = phi
+        k1 = st2.copy()
+        k1.engine.kron_low(phi)
+        k1.phys = [p + 2 for p in st2.phys] + [1, 0]
+        k1.n, k1.n_local = n + 2, st2.n_local + 2
+        results['kron_right'] = k1.to_column_vector()
+        k2 = st2.copy()
+        k2.engine.kron_low(phi)
+        k2.phys = [1, 0] + [p + 2 for p in st2.phys]
+        k2.n, k2.n_local = n + 2, st2.n_local + 2
+        results['kron_left'] = k2.to_column_vector()
+        if rank == 0:
+            out.put((vec, U, results))
+    finally:
+        dist.destroy_process_group()
+
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_dropin_state_over_gloo(world):
+    """from_column_vector / Operator.__call__ / marginals / measure (keep + remove, rank-bit + local qubits) /
+    tensor product of a ShardedState against the oracle, world_size 2 and 4 on gloo."""
+    n = 9
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dropin_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    vec, U, res = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.max(np.abs(res['roundtrip'] - vec)) < 1e-13
+    assert np.max(np.abs(res['untouched'] - vec)) < 1e-13
+    want = orc.apply_matrix_flat(U, vec, [n - 1 - 0, n - 1 - (n - 2)], renorm=True)
+    assert np.max(np.abs(res['applied'] - want)) < 1e-12
+    ps, _, _ = orc.measurement_probabilities(want.reshape([2] * n), [n - 1, 0, 3])
+    assert np.max(np.abs(res['marg'] - ps)) < 1e-12
+    for qs, remove, u, bits, post, rank_after in res['measure']:
+        qi = list(range(n)) if qs is None else qs
+        bits_want, post_want = orc.measure(want.reshape([2] * n), qi, u, remove=remove)
+        assert tuple(bits) == tuple(bits_want), (qs, remove)
+        assert rank_after == (n - len(qi) if remove else n)
+        assert np.max(np.abs(post - post_want.reshape(-1))) < 1e-12, (qs, remove)
+    b, post = res['int_result']
+    np.random.seed(123)
+    bits_want, post_want = orc.measure(want.reshape([2] * n), [1], float(np.random.random_sample()), remove=False)
+    assert b == bits_want[0] and isinstance(b, (int, np.integer))
+    assert np.max(np.abs(post - post_want.reshape(-1))) < 1e-12
+    assert np.max(np.abs(res['kron_right'] - np.kron(want, res['phi']))) < 1e-12
+    assert np.max(np.abs(res['kron_left'] - np.kron(res['phi'], want))) < 1e-12

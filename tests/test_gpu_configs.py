@@ -36,7 +36,7 @@ def test_config1_grover_d10_finds_the_marked_item():
     assert iterations == 25
     for _ in range(iterations):
         state = Grover(state)
-    ps = state._measurement_probabilities(list(range(d)))
+    ps = state.marginal_probabilities(list(range(d)))
     want = sum(((marked >> i) & 1) << (d - 1 - i) for i in range(d))      # f's bit order: bit i of the index = qubit i
     assert ps[want] > 0.99
     np.random.seed(3)
@@ -74,13 +74,13 @@ def test_config3_phase_estimation_gate_by_gate(t, dtype):
     passes, gates = c.stats(dtype)
     assert passes < gates / 3                       # the controlled phases ride along in fused passes
     qi = list(range(min(t, 10)))
-    ps = out._measurement_probabilities(qi)
+    ps = out.marginal_probabilities(qi)
     want = int(''.join(str(b) for b in phi_bits[:len(qi)]), 2)
     tol = 1e-3 if dtype == np.complex64 else 1e-9
     assert ps[want] > 1 - tol
     rest = list(range(len(qi), t))
     if rest:
-        ps2 = out._measurement_probabilities(rest[:10])
+        ps2 = out.marginal_probabilities(rest[:10])
         assert ps2[int(''.join(str(b) for b in phi_bits[len(qi):len(qi) + len(rest[:10])]), 2)] > 1 - tol
 
 
@@ -101,7 +101,7 @@ def test_config5_density_operator_14_qubits():
     assert abs(p_rho.sum() - 1) < 1e-10
     assert np.max(np.abs(p_rho - p_psi)) < 1e-12
     ps, _ = rho._measurement_probabilities([13, 0, 6])
-    assert np.max(np.abs(ps - psi._measurement_probabilities([13, 0, 6]))) < 1e-12
+    assert np.max(np.abs(ps - psi.marginal_probabilities([13, 0, 6]))) < 1e-12
     u = 0.61
     assert rho.measure([13, 0, 6], u=u) == psi.measure([13, 0, 6], u=u)
     assert np.max(np.abs(rho.probabilities - psi.probabilities)) < 1e-12

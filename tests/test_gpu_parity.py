@@ -261,7 +261,7 @@ def test_marginals_and_collapse_random_subsets(dtype):
         for m in (1, 2, 3, min(n, 11), n):
             qi = [int(q) for q in rng.permutation(n)[:m]]
             s = _state(vec, dtype)
-            ps = s._measurement_probabilities(qi)
+            ps = s.marginal_probabilities(qi)
             want_ps, _, _ = orc.measurement_probabilities(vec.reshape([2] * n), qi)
             assert np.max(np.abs(ps - want_ps)) < tol
             for remove in (False, True):
@@ -518,7 +518,7 @@ def test_full_size_properties(dtype, n):
     for q in range(n):
         c.append(H, [q])
     s = c.run(qc.zeros(n, dtype=dtype))
-    ps = s._measurement_probabilities([0, n // 2, n - 1])
+    ps = s.marginal_probabilities([0, n // 2, n - 1])
     assert np.max(np.abs(ps - 1 / 8)) < tol
     sample = s._dv.buf[:64].cpu().numpy().view(dtype)
     scale = 1 / np.sqrt(float(s._dv.norm[0].item()))
@@ -535,7 +535,7 @@ def test_full_size_properties(dtype, n):
         both.append(operator_for(name, theta).adj, list(qs))
     z = qc.zeros(n, dtype=dtype)
     back = both.run(z)
-    ps = back._measurement_probabilities(list(range(0, n, 3)))
+    ps = back.marginal_probabilities(list(range(0, n, 3)))
     assert abs(ps[0] - 1.0) < tol and abs(ps.sum() - 1.0) < tol
     amp0 = back._dv.buf[:2].cpu().numpy().view(dtype)[0] / np.sqrt(float(back._dv.norm[0].item()))
     assert abs(abs(amp0) - 1.0) < tol
@@ -543,8 +543,8 @@ def test_full_size_properties(dtype, n):
     a = fwd.run(z, fuse=True)
     b = fwd.run(z, fuse=False)
     qi = [0, 5, n - 1, n - 2, 11]
-    assert np.max(np.abs(a._measurement_probabilities(qi) - b._measurement_probabilities(qi))) < tol
+    assert np.max(np.abs(a.marginal_probabilities(qi) - b.marginal_probabilities(qi))) < tol
     assert abs(a.dot(b) - 1.0) < tol
     # measurement at full size: outcome is consistent with the marginals and collapses the state
     bits = a.measure(qi, u=0.5)
-    assert a._measurement_probabilities(qi)[int(''.join(map(str, bits)), 2)] > 1 - tol
+    assert a.marginal_probabilities(qi)[int(''.join(map(str, bits)), 2)] > 1 - tol

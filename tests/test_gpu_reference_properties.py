@@ -153,7 +153,7 @@ def test_density_operator_is_the_ensemble_of_states():
         want = qc.DensityOperator.from_ensemble([U(s, qubit_indices=qi) for s in states], ps)
         np.testing.assert_allclose(U(rho, qubit_indices=qi)._t, want._t, atol=1e-12)
         mq = [int(q) for q in rng.permutation(d)[:2]]
-        mix = sum(p * s._measurement_probabilities(mq) for p, s in zip(ps, states))
+        mix = sum(p * s.marginal_probabilities(mq) for p, s in zip(ps, states))
         np.testing.assert_allclose(rho._measurement_probabilities(mq)[0], mix, atol=1e-12)
         r2 = copy.deepcopy(rho)
         r2.permute_qubits(list(range(d))[::-1]).permute_qubits(list(range(d))[::-1], inverse=True)

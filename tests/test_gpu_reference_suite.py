@@ -20,7 +20,7 @@ REF_TESTS = os.path.join(ROOT, 'oracle', '_ref', 'tests')
 BOOT = r'''
 import sys, warnings
 warnings.simplefilter('ignore')
-sys.path.insert(0, %(root)r)
+sys.path.append(%(root)r)
 import qcircuits_b200
 qcircuits_b200.install_as_qcircuits()
 import qcircuits
@@ -51,7 +51,7 @@ def test_the_reference_suite_passes_unmodified_on_the_engine():
 SAMPLING = r'''
 import sys, warnings
 warnings.simplefilter('ignore')
-sys.path.insert(0, %(root)r)
+sys.path.append(%(root)r)       # after the working directory: `from tests import random_state` must find ./tests.py
 import qcircuits_b200
 qcircuits_b200.install_as_qcircuits()
 import types

@@ -30,7 +30,7 @@ def test_marginals_of_large_states_every_bit_class(dtype):
                  list(range(n - 1, n - 11, -1)), list(range(0, 10)), [int(q) for q in rng.permutation(n)[:7]],
                  [int(q) for q in rng.permutation(n)[:12]], [int(q) for q in rng.permutation(n)[:n - 1]]]
         for qi in cases:
-            ps = s._measurement_probabilities(qi)
+            ps = s.marginal_probabilities(qi)
             rest = tuple(a for a in range(n) if a not in qi)
             want = np.transpose(t.sum(axis=rest) if rest else t, np.argsort(np.argsort(qi))).reshape(-1)
             assert np.max(np.abs(ps - want)) < tol, (n, qi)
