@@ -138,6 +138,19 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def sharded_parity_check():
+    """Before the multi-GPU timing: ShardedState (circuit with exchanges, Operator.__call__, marginals, measure, tensor
+    product) against the ORACLE at 14 and 19 qubits on this very process group (tools/dist_check.py; the oracle is the
+    checker here, never the thing measured).  Returns the record that goes into the line as `parity`."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('dist_check', os.path.join(ROOT, 'tools', 'dist_check.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    worst = mod.check(max_n=19, verbose=False)
+    return {'checked_against': 'oracle/qc_oracle.py', 'qubits': [14, 19], 'dtypes': ['c64', 'c128'],
+            'worst_error_over_tolerance': worst, 'tolerance': {'c64': 1e-5, 'c128': 1e-12}, 'ok': bool(worst < 1.0)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -152,6 +165,10 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=24.0, help='seconds of CPU work per reference sample')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-strong', action='store_true', help='skip the 33-qubit strong-scaling leg')
+    ap.add_argument('--skip-configs', action='store_true', help='skip the short runs of BASELINE configs 2, 3 and 5')
+    ap.add_argument('--strong-qubits', type=int, default=33)
+    ap.add_argument('--skip-parity', action='store_true', help='multi-GPU: skip the sharded-vs-oracle check before timing')
     ap.add_argument('--workload', default='layered', choices=['layered', 'qpe'],
                     help='layered = the headline random circuit; qpe = BASELINE config 3 (phase estimation + inverse QFT)')
     args = ap.parse_args()
@@ -166,7 +183,7 @@ def main():
         return reference_arm(args)
     if world > 1:
         from qcircuits_b200 import dist_bench
-        return dist_bench.main(args)
+        return dist_bench.main(args, parity_check=None if args.skip_parity else sharded_parity_check)
 
     import torch
     import qcircuits_b200 as qc
@@ -264,6 +281,76 @@ def main():
     if not args.skip_cpu:        # the cpu_baseline leg: the only use of oracle/ here
         cpu = cpu_reference_rate(n, depth, args.cpu_budget)
 
+    # ---- the other BASELINE configs and the strong-scaling leg, each a short device-resident run ----------------
+    del out, state0
+    torch.cuda.empty_cache()
+
+    def timed_run(circuit, make_state, reps, dtype):
+        s0 = make_state()
+        res = circuit.run(s0)                                 # warm-up (plans, first touch)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            res = None                                        # (never two results alive: 33 qubits = 64 GiB each)
+            res = circuit.run(s0)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        npass, ng = circuit.stats(dtype)
+        return res, {'ms_per_step': ms, 'gates': ng, 'passes': npass, 'gates_per_s': ng / (ms * 1e-3)}
+
+    strong = None
+    if not args.skip_strong and qpe is None and args.dtype == 'c64' and torch.cuda.mem_get_info()[0] > 140 * 2 ** 30:
+        ns = args.strong_qubits
+        cs = layered_circuit(ns, depth, seed=SEED)
+        res, strong = timed_run(cs, lambda: qc.zeros(ns, dtype=np.complex64), 2, np.complex64)
+        strong.update({'qubits': ns, 'amp_updates_per_s_per_gpu': strong['gates'] * 2.0 ** ns / (strong['ms_per_step'] * 1e-3),
+                       'what': 'the same 33-qubit circuit the multi-GPU lines run sharded (strong scaling, N = 1 leg)'})
+        del res, cs
+        torch.cuda.empty_cache()
+    configs = None
+    if not args.skip_configs and qpe is None and args.dtype == 'c64' and n == 30:
+        configs = {}
+        c2 = layered_circuit(28, 40, seed=SEED)
+        res, rec = timed_run(c2, lambda: qc.zeros(28, dtype=np.complex128), 3, np.complex128)
+        rec.update({'workload': 'config 2: layered circuit, 28 qubits complex128, depth 40',
+                    'hbm_GBs': 2.0 * 2 ** 28 * 16 * rec['passes'] / (rec['ms_per_step'] * 1e-3) / 1e9})
+        configs['config2_28q_c128'] = rec
+        del res, c2
+        torch.cuda.empty_cache()
+        if torch.cuda.mem_get_info()[0] > 70 * 2 ** 30:
+            from qcircuits_b200.workloads import phase_estimation_circuit
+            c3, eigvec, phase = phase_estimation_circuit(30, seed=SEED)
+            res, rec = timed_run(c3, lambda: qc.zeros(30, dtype=np.complex64) * qc.State(eigvec.reshape(2, 2), dtype=np.complex64),
+                                 1, np.complex64)
+            ps = res.marginal_probabilities(list(range(12)))
+            rec.update({'workload': 'config 3: phase estimation of a seeded 2-qubit unitary, t = 30, 32 qubits complex64',
+                        'true_phase': phase, 'estimated_phase_12_bits': int(np.argmax(ps)) / 4096.0,
+                        'peak_probability': float(ps.max())})
+            configs['config3_qpe_32q_c64'] = rec
+            del res, c3
+            torch.cuda.empty_cache()
+        from qcircuits_b200.workloads import layered_gate_list, operator_for
+        rho = qc.zeros(14).density_operator()
+        glist = [(operator_for(nm, th), list(qs)) for nm, th, qs in layered_gate_list(14, 10, seed=SEED)]
+        for op, qs in glist[:20]:
+            rho = op(rho, qubit_indices=qs)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for op, qs in glist[20:]:
+            rho = op(rho, qubit_indices=qs)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        configs['config5_rho_14q_c128'] = {
+            'workload': 'config 5: U rho U^dagger gate by gate (Operator.__call__), 14 qubits = rank-28 tensor complex128, depth 10',
+            'gates': len(glist) - 20, 'ms_total': ms, 'gates_per_s': (len(glist) - 20) / (ms * 1e-3),
+            'hbm_GBs': 2.0 * 2 ** 28 * 16 * (len(glist) - 20) / (ms * 1e-3) / 1e9, 'trace': float(rho.probabilities.sum())}
+        del rho
+        torch.cuda.empty_cache()
+
     line = {
         'metric': 'gates/s, random layered circuit', 'value': value, 'unit': 'gates/s', 'n_gpus': 1,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -281,6 +368,8 @@ def main():
                      'ms_per_launch': ms_per_step / passes, 'frac_of_8TBs_nominal': achieved / 8000.0},
         'roofline_per_gate_pass': per_gate,
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': passes * args.steps,
+        'amp_updates_per_s_per_gpu': ngates * 2.0 ** n / (ms_per_step * 1e-3),
+        'strong_scaling': strong, 'other_configs': configs,
         'clocks': clocks.summary(), 'step_ms': step_ms, 'norm_check': probs_sum,
     }
     if qpe is not None:

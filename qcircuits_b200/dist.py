@@ -199,15 +199,22 @@ class CudaEngine:
         else:
             _lib.check(lib.qcs_set_basis(self.buf.data_ptr(), self.n_local, self.code, index, _lib.stream_ptr()))
 
-    def run_local(self, rank_gates, max_ops):
+    def compile_local(self, rank_gates, max_ops):
+        """schedule + plan the fused passes of a communication-free step once (ShardedState.run caches the result)"""
         from .circuit import build_passes
+        groups = schedule_passes(rank_gates, self.n_local, self.dtype, max_ops=max_ops)
+        return build_passes(rank_gates, groups, self.n_local, self.dtype)
+
+    def run_compiled(self, passes):
         lib = _lib.load()
         ws = _lib.workspace().data_ptr()
-        groups = schedule_passes(rank_gates, self.n_local, self.dtype, max_ops=max_ops)
-        for ops, keep, _ in build_passes(rank_gates, groups, self.n_local, self.dtype):
+        for ops, keep, _ in passes:
             _lib.check(lib.qcs_apply_fused(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, ops,
                                            len(ops), None, None, ws, _lib.stream_ptr()))
             self.launches += 1
+
+    def run_local(self, rank_gates, max_ops):
+        self.run_compiled(self.compile_local(rank_gates, max_ops))
 
     def permute(self, src_bit):
         _lib.check(_lib.load().qcs_permute_bits(self.spare.data_ptr(), self.buf.data_ptr(), self.n_local, self.code,
@@ -321,23 +328,42 @@ class ShardedState:
 
     def run(self, circuit, max_ops=128):
         """Apply a Circuit (its gates are on logical qubits).  Collective: every rank calls it."""
-        gates = [_LogicalGate(gt.plan, [circuit.n - 1 - b for b in gt.bits]) for gt in circuit.gates]
-        steps, phys = dist_schedule(gates, self.n, self.g, self.phys)
-        for step in steps:
-            if step[0] == 'local':
-                rank_gates = []
-                for idx, bits in step[1]:
-                    sp = specialize(gates[idx].plan, bits, self.n_local, self.proc_rank)
-                    if sp is not None:
-                        rank_gates.append(_Gate(None, sp[1], plan=sp[0]))
-                if rank_gates:
-                    self.engine.run_local(rank_gates, max_ops)
+        # the plan -- exchange schedule, rank-specialised gates, fused passes -- depends only on the circuit and the
+        # layout it starts from: built once per (circuit, layout), like Circuit._plans on one GPU
+        key = (id(circuit), len(circuit.gates), tuple(self.phys), max_ops, self.n_local)
+        cache = self.__dict__.setdefault('_plans', {})
+        plan = cache.get(key)
+        if plan is None:
+            gates = [_LogicalGate(gt.plan, [circuit.n - 1 - b for b in gt.bits]) for gt in circuit.gates]
+            steps, phys = dist_schedule(gates, self.n, self.g, self.phys)
+            compiled = []
+            for step in steps:
+                if step[0] == 'local':
+                    rank_gates = []
+                    for idx, bits in step[1]:
+                        sp = specialize(gates[idx].plan, bits, self.n_local, self.proc_rank)
+                        if sp is not None:
+                            rank_gates.append(_Gate(None, sp[1], plan=sp[0]))
+                    if rank_gates:
+                        if hasattr(self.engine, 'compile_local'):
+                            compiled.append(('passes', self.engine.compile_local(rank_gates, max_ops)))
+                        else:
+                            compiled.append(('gates', rank_gates))
+                else:
+                    compiled.append(step)
+            plan = cache[key] = (compiled, phys, circuit)          # (the circuit is kept alive: its id is the key)
+        compiled, phys, _ = plan
+        for step in compiled:
+            if step[0] == 'passes':
+                self.engine.run_compiled(step[1])
+            elif step[0] == 'gates':
+                self.engine.run_local(step[1], max_ops)
             elif step[0] == 'lperm':
                 self.engine.permute(step[1])
             else:
                 self.engine.exchange(self.group)
                 self.exchanges += 1
-        self.phys = phys
+        self.phys = list(phys)
         self.norm = None
         return self
 
