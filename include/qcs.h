@@ -101,6 +101,11 @@ int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *
  * a (the arm table of csrc/gen_regops.py, a < 108).  `stats` has 128 entries. */
 int qcs_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
 
+/* Planning only: as qcs_plan_stats, plus the sweep that executes each input op: sweep_of_op[i] = index of the sweep
+ * (execution order), + 1000 when that sweep applies a tensor-core block.  The fusion scheduler uses it to cut a pass
+ * after its last tensor-core sweep (ops of later sweeps are last in execution order and may move to the next pass). */
+int qcs_plan_order(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats, int32_t *sweep_of_op);
+
 /* Planning only, complex64: the tensor-core sweeps of the pass (north_star (1): "fused blocks ... run on tensor
  * cores").  A sweep multiplies a run of gates into one dense 2^5 x 2^5 block on five tile bits (the contraction
  * of operators.py:261 for all of them at once) and applies it with tcgen05.mma kind::tf32 as a 3-term split.

@@ -60,6 +60,7 @@ def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None,
         low_shrink = int(os.environ.get('QCS_LOW_SHRINK', '6'))
     if tail_trim is None:
         tail_trim = int(os.environ.get('QCS_TAIL_TRIM', '8'))
+    block_cut = int(os.environ.get('QCS_BLOCK_CUT', '0')) != 0
     geoms = []
     if high_bits is not None:
         geoms.append((min(low, n), max(0, min(high_bits, n - min(low, n)))))
@@ -126,11 +127,47 @@ def schedule_passes(gates, n, dtype, max_ops=128, lookahead=512, high_bits=None,
             # a gate whose dense targets exceed the preferred tile even alone: libqcs shrinks the low run
             best = [remaining[0]]
         if tail_trim > 0 and len(best) > 1:
-            best = _trim_tail_sweep(gates, best, n, dtype, tail_trim)
+            cut = _cut_after_last_block(gates, best, n, dtype) if block_cut else None
+            best = cut if cut is not None else _trim_tail_sweep(gates, best, n, dtype, tail_trim)
         passes.append(best)
         chosen = set(best)
         remaining = [i for i in remaining if i not in chosen]
     return passes
+
+
+def _commutes_past_the_rest(gates, group, drop):
+    """True if every op of ``group`` listed in ``drop`` (positions) may run after all kept ops that follow it in
+    program order: no shared bit on which either acts non-diagonally."""
+    for k in sorted(drop):
+        a = gates[group[k]]
+        for j in range(k + 1, len(group)):
+            if j in drop:
+                continue
+            b = gates[group[j]]
+            if (a.nd_mask & (b.nd_mask | b.d_mask)) or (a.d_mask & b.nd_mask):
+                return False
+    return True
+
+
+def _cut_after_last_block(gates, group, n, dtype):
+    """Passes of the tensor-core kernel hold at most four dense blocks.  What the planner cannot put into them runs
+    as register sweeps AFTER the last block, at ~1.3 ms per sweep + 0.1 ms per op (30 qubits) where a block costs
+    ~1.2 ms for ~20 ops: those ops are handed back to the scheduler -- they are last in the pass's execution order, so
+    they may open the next pass instead, where they join its blocks.  Returns the shortened group, or None when the
+    pass has no block (complex128, small states) or nothing runs after its last block."""
+    lib = _lib.load()
+    stats = (ctypes.c_int32 * 128)()
+    order = (ctypes.c_int32 * len(group))()
+    ops, keep = make_ops([(gates[i].plan, gates[i].bits, False) for i in group])
+    if lib.qcs_plan_order(n, _lib.dtype_code(dtype), ops, len(ops), stats, order) != 0:
+        return None
+    if (stats[7] & 255) == 0:
+        return None
+    last_block = max(o - 1000 for o in order if o >= 1000)
+    drop = {k for k, o in enumerate(order) if 0 <= o < 1000 and o > last_block}
+    if not drop or len(drop) >= len(group) or not _commutes_past_the_rest(gates, group, drop):
+        return None if not drop else group
+    return [g for k, g in enumerate(group) if k not in drop]
 
 
 def _trim_tail_sweep(gates, group, n, dtype, max_tail):

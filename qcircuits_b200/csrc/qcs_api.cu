@@ -97,6 +97,12 @@ int qcs_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats
     return tile_plan_stats(n, dtype, ops, nops, stats);
 }
 
+int qcs_plan_order(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats, int32_t *sweep_of_op) {
+    if (!ops || !stats || !sweep_of_op) return set_error(QCS_ERR_ARG, "null argument");
+    if (nops < 1 || nops > QCS_MAX_OPS) return set_error(QCS_ERR_ARG, "nops must be in 1..QCS_MAX_OPS");
+    return tile_plan_order(n, dtype, ops, nops, stats, sweep_of_op);
+}
+
 int qcs_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info) {
     if (!ops || !stats || !images || !info) return set_error(QCS_ERR_ARG, "null argument");
     if (nops < 1 || nops > QCS_MAX_OPS) return set_error(QCS_ERR_ARG, "nops must be in 1..QCS_MAX_OPS");

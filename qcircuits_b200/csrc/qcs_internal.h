@@ -113,6 +113,7 @@ int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, 
                double *norm_out, void *ws, cudaStream_t stream);
 
 int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
+int tile_plan_order(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats, int32_t *sweep_of_op);
 int tile_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info);
 
 int misc_set_basis(void *buf, int n, int dtype, uint64_t index, cudaStream_t st);

@@ -796,6 +796,7 @@ struct HostOp {            // one entry of the caller's list, classified
 }  // namespace
 
 // ---- tensor-core blocks: host side ----------------------------------------------------------------
+static thread_local int32_t *g_sweep_of_op = nullptr;           // set by tile_plan_order: sweep index of every input op
 static thread_local unsigned char *g_block_dump = nullptr;     // set by tile_plan_blocks (diagnostics / tests)
 static thread_local int32_t *g_block_info = nullptr;
 
@@ -1181,6 +1182,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
             sw.kind = SWEEP_GENERIC; sw.first = P.ngen; sw.count = 1; sw.nreg = 0;
             ++P.ngen; ++P.nsweeps;
             n_last_sweep = 1; last_sweep_ops[0] = first;        // this op IS the most recent sweep
+            if (g_sweep_of_op) g_sweep_of_op[first] = P.nsweeps - 1;
             for (int i = 1; i < npend; ++i) pending[i - 1] = pending[i];
             --npend;
             continue;
@@ -1323,6 +1325,9 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         n_last_sweep = ntaken + nblk;
         for (int t = 0; t < ntaken; ++t) last_sweep_ops[t] = taken[t];
         for (int t = 0; t < nblk; ++t) last_sweep_ops[ntaken + t] = blk_ops[t];
+        if (g_sweep_of_op) {                    // (tensor-core sweeps are reported as 1000 + index)
+            for (int t = 0; t < ntaken + nblk; ++t) g_sweep_of_op[last_sweep_ops[t]] = P.nsweeps + (tc_sweep ? 1000 : 0);
+        }
         for (int t = 0; t < ntaken; ++t) {
             const qcs_op &o = ops[taken[t]];
             if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
@@ -1561,6 +1566,15 @@ int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stat
         if (rc != QCS_ERR_UNSUPPORTED) return rc;
     }
     return build_and_launch<LargeProg>(nullptr, nullptr, n, dtype, ops, nops, nullptr, nullptr, nullptr, nullptr, stats);
+}
+
+int tile_plan_order(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats, int32_t *sweep_of_op) {
+    if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
+    for (int i = 0; i < nops; ++i) sweep_of_op[i] = -1;
+    g_sweep_of_op = sweep_of_op;
+    const int rc = tile_plan_stats(n, dtype, ops, nops, stats);
+    g_sweep_of_op = nullptr;
+    return rc;
 }
 
 int tile_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info) {
