@@ -10,6 +10,9 @@ The tests are exact (== 0, == 1): the factories of operators.py produce exact ze
 import numpy as np
 
 
+ANALYZE_MAX_QUBITS = 6        # wider operators are dense-kernel operands: no structure analysis (Operator._plan)
+
+
 class GatePlan:
     __slots__ = ('k', 'controls', 'targets', 'diagonal', 'matrix', 'full')
 

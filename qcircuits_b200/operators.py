@@ -228,9 +228,21 @@ class Operator(OperatorBase):
         return dev
 
     def _plan(self):
-        """Structure of the matrix, cached: see _gates.analyze."""
+        """Structure of the matrix, cached: see _gates.analyze.  Operators wider than the tile engine's ops go to the
+        dense kernel, which has no use for control / target structure: they skip the analysis (a scan per qubit of
+        a 2^k x 2^k matrix -- it was 2/3 of the run time of examples/grover_algorithm.py at d = 10) and only learn
+        whether they are diagonal, in one pass."""
         if self._plan_cache is None:
-            self._plan_cache = _gates.analyze(np.ascontiguousarray(self.to_matrix()))
+            M = np.ascontiguousarray(self.to_matrix())
+            k = self.rank // 2
+            if k > _gates.ANALYZE_MAX_QUBITS:
+                diag = np.diag(M)
+                if np.count_nonzero(M) == np.count_nonzero(diag):
+                    self._plan_cache = _gates.GatePlan(k, [], list(range(k)), True, np.ascontiguousarray(diag), M)
+                else:
+                    self._plan_cache = _gates.GatePlan(k, [], list(range(k)), False, M, M)
+            else:
+                self._plan_cache = _gates.analyze(M)
         return self._plan_cache
 
 
