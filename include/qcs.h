@@ -142,6 +142,14 @@ int qcs_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype,
 int qcs_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t *src_bit,
                      qcs_stream stream);
 
+/* U_f applied to a State (operators.py:809-853 builds the 2^d x 2^d permutation tensor with a Python loop and contracts
+ * it with np.tensordot, :261): dst[i] = src[i XOR (f(x(i)) << tbit)] / sqrt(*norm_in), where x(i) gathers the flat bits
+ * xbits[0..nx-1] of i (xbits[0] = most significant bit of x) and f is a packed truth table on the device (bit x of
+ * dev_table: word x >> 5, bit x & 31).  A permutation: the squared norm of dst is that of src (1 after the scale).
+ * dst must not alias src. */
+int qcs_apply_uf(void *dst, const void *src, int n, int dtype, const uint32_t *dev_table, const int32_t *xbits,
+                 int nx, int tbit, const double *norm_in, qcs_stream stream);
+
 /* State factories zeros/ones/bitstring (state.py:455-551): buf = 0 except buf[index] = 1. */
 int qcs_set_basis(void *buf, int n, int dtype, uint64_t index, qcs_stream stream);
 

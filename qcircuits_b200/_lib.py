@@ -34,6 +34,7 @@ PROTOTYPES = {
     'qcs_version': (c_int, []),
     'qcs_last_error': (ctypes.c_char_p, []),
     'qcs_workspace_bytes': (ctypes.c_int64, []),
+    'qcs_apply_uf': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'qcs_plan_order': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     'qcs_plan_blocks': (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'qcs_tile_limits': (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -189,6 +189,14 @@ int qcs_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t
     return misc_permute(dst, src, n, dtype, src_bit, (cudaStream_t)stream);
 }
 
+int qcs_apply_uf(void *dst, const void *src, int n, int dtype, const uint32_t *dev_table, const int32_t *xbits, int nx,
+                 int tbit, const double *norm_in, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(src, n, dtype)) return e;
+    if (!dev_table || !xbits) return set_error(QCS_ERR_ARG, "null argument");
+    return misc_apply_uf(dst, src, n, dtype, dev_table, xbits, nx, tbit, norm_in, (cudaStream_t)stream);
+}
+
 int qcs_set_basis(void *buf, int n, int dtype, uint64_t index, qcs_stream stream) {
     if (int e = check_state(buf, n, dtype)) return e;
     return misc_set_basis(buf, n, dtype, index, (cudaStream_t)stream);

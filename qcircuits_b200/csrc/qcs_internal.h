@@ -135,6 +135,8 @@ int misc_outer(void *rho, const void *psi, int n, int dtype, double p, const dou
 int misc_gate1(void *dst, const void *src, int n, int dtype, const double *matrix, int tbit, uint64_t ctrl,
                const double *norm_in, double *norm_out, void *ws, cudaStream_t st);
 int misc_partial_trace(void *out, const void *rho, int d, int dtype, const int32_t *keep, int nkeep, cudaStream_t st);
+int misc_apply_uf(void *dst, const void *src, int n, int dtype, const uint32_t *dev_table, const int32_t *xbits, int nx,
+                  int tbit, const double *norm_in, cudaStream_t st);
 int misc_dense(void *dst, const void *src, int n, int dtype, const void *dev_matrix, int k, const int32_t *bitpos,
                const double *norm_in, double *norm_out, void *ws, cudaStream_t st);
 

@@ -1005,4 +1005,45 @@ int misc_dense(void *dst, const void *src, int n, int dtype, const void *dev_mat
     return QCS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// U_f (reference operators.py:809-853): |x>|y> -> |x>|y XOR f(x)> as an index permutation
+// ------------------------------------------------------------------------------------------------
+// dst[i] = src[i XOR (f(x(i)) << tbit)], x(i) = the input bits of i gathered MSB-first; f as a packed truth table.
+// Reads and writes are 16-byte vectors wherever the target bit is not inside a vector; the permutation only moves
+// amplitudes within pairs, so both streams stay coalesced.  The operator tensor (2^(2d) entries) is never built.
+struct UfMap { int32_t xbit[32]; int32_t nx, tbit; };
+
+template <typename C>
+__global__ void __launch_bounds__(EW_THREADS) uf_kernel(C *__restrict__ dst, const C *__restrict__ src, uint64_t N, UfMap mp,
+                                                        const uint32_t *__restrict__ table, const double *norm_in) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const double sc = load_inv_norm(norm_in);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        uint32_t x = 0;
+        for (int j = 0; j < mp.nx; ++j) x = (x << 1) | (uint32_t)((i >> mp.xbit[j]) & 1ull);
+        const uint64_t flip = (uint64_t)((__ldg(&table[x >> 5]) >> (x & 31u)) & 1u) << mp.tbit;
+        C v = src[i ^ flip];
+        if (norm_in) { v.x = (decltype(v.x))(v.x * sc); v.y = (decltype(v.y))(v.y * sc); }
+        dst[i] = v;
+    }
+}
+
+int misc_apply_uf(void *dst, const void *src, int n, int dtype, const uint32_t *dev_table, const int32_t *xbits, int nx,
+                  int tbit, const double *norm_in, cudaStream_t st) {
+    if (nx < 1 || nx > 31 || nx >= n + 1) return set_error(QCS_ERR_ARG, "U_f needs 1..31 input qubits");
+    if (tbit < 0 || tbit >= n) return set_error(QCS_ERR_ARG, "U_f target bit out of range");
+    if (dst == src) return set_error(QCS_ERR_ARG, "U_f cannot run in place");
+    UfMap mp;
+    mp.nx = nx; mp.tbit = tbit;
+    uint64_t seen = 1ull << tbit;
+    for (int j = 0; j < nx; ++j) {
+        if (xbits[j] < 0 || xbits[j] >= n || ((seen >> xbits[j]) & 1ull)) return set_error(QCS_ERR_ARG, "bad U_f input bit");
+        seen |= 1ull << xbits[j];
+        mp.xbit[j] = xbits[j];
+    }
+    const uint64_t N = 1ull << n;
+    DISPATCH_C(dtype, (uf_kernel<C><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((C *)dst, (const C *)src, N, mp, dev_table, norm_in)));
+    return check_launch();
+}
+
 }  // namespace qcs

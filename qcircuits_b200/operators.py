@@ -353,16 +353,75 @@ def ControlledU(U):
     return Operator(t)
 
 
+class UfOperator(Operator):
+    """U_f tagged at construction: the Boolean function is kept as a truth table and applied to a State as
+    an index permutation (qcs_apply_uf) -- the 2^(2d)-entry tensor of reference operators.py:809-853 is only built if
+    somebody reads ``_t`` (composition with another operator, to_matrix, a DensityOperator argument), and any in-place
+    change of the tensor (permute_qubits, swap_qubits, assignment) turns it back into an ordinary Operator."""
+
+    def __init__(self, table, d=None):
+        self._dev_table = {}
+        if d is None:
+            # ``op.__class__(tensor)`` -- how the base classes build results (.adj, composition): an ordinary operator
+            Operator.__init__(self, table)
+            self._uf_d = self._tensor.ndim // 2
+            self._uf_table = None
+            return
+        self._uf_table = np.ascontiguousarray(table, dtype=np.uint8)       # f over the 2^(d-1) inputs, x MSB-first
+        self._uf_d = d
+        self._tensor = None
+        self._plan_cache = None
+        self._dev_matrix = {}
+
+    @property
+    def _t(self):
+        if self._tensor is None:
+            d = self._uf_d
+            cols = np.arange(2 ** d)
+            rows = (cols & ~1) | ((cols & 1) ^ self._uf_table[cols >> 1])
+            M = np.zeros((2 ** d, 2 ** d), dtype=np.complex128)
+            M[rows, cols] = 1.0
+            interleave = np.arange(2 * d).reshape(2, d).T.reshape(-1)
+            self._tensor = np.reshape(M, [2] * (2 * d)).transpose(interleave)
+        return self._tensor
+
+    @_t.setter
+    def _t(self, value):
+        Operator._t.fset(self, value)
+        self._uf_table = None            # no longer known to be U_f
+
+    @property
+    def shape(self):
+        return (2,) * (2 * self._uf_d) if self._tensor is None else self._tensor.shape
+
+    def _device_table(self):
+        from . import _lib
+        t = _lib.require_cuda()
+        key = t.cuda.current_device()
+        dev = self._dev_table.get(key)
+        if dev is None:
+            bits = np.zeros(((self._uf_table.size + 31) // 32) * 32, dtype=np.uint8)
+            bits[:self._uf_table.size] = self._uf_table
+            words = np.packbits(bits.reshape(-1, 32)[:, ::-1], axis=1).view('>u4').astype(np.uint32).reshape(-1)
+            dev = self._dev_table[key] = t.from_numpy(words.view(np.int32)).to('cuda')
+        return dev
+
+    def _apply(self, arg, qubit_indices=None):
+        if isinstance(arg, State) and self._uf_table is not None:
+            qi = _validated_indices(self._uf_d, arg.rank, qubit_indices)
+            return arg._apply_uf(self, qi)
+        return super()._apply(arg, qubit_indices)
+
+
 def U_f(f, d):
     """d-qubit operator flipping the last qubit when the Boolean f of the first d-1 bits is 1."""
     if d < 2:
         raise ValueError('U_f operator requires rank >= 2.')
-
-    def image(bits):
-        r = f(*bits[:-1])
+    table = np.zeros(2 ** (d - 1), dtype=np.uint8)
+    for x, bits in enumerate(product([0, 1], repeat=d - 1)):
+        r = f(*bits)
         if r not in [0, 1]:
             raise RuntimeError('Function f for U_f operator should be Boolean,'
                                'i.e., return 0 or 1.')
-        return bits[:-1] + ((1 - bits[-1]) if r else bits[-1],)
-
-    return _from_basis_map(d, image)
+        table[x] = r
+    return UfOperator(table, d)

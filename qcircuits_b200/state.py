@@ -207,6 +207,18 @@ class State(Tensor):
             return State(self._dv.apply_ops(ops, keep))
         return State(self._dv.apply_dense(op._device_matrix(self._dv.dtype), plan.k, bits))
 
+    def _apply_uf(self, op, qubit_indices):
+        """U_f on the listed qubits as an index permutation (operators.UfOperator; reference operators.py:809-853 +
+        :261): the first d-1 listed qubits are f's arguments (first = most significant), the last one is flipped."""
+        d = self.rank
+        bits = [d - 1 - q for q in qubit_indices]
+        src = self._dv
+        dst = src._new_like()
+        _lib.check(_lib.load().qcs_apply_uf(dst.buf.data_ptr(), src.buf.data_ptr(), d, src.code, op._device_table().data_ptr(),
+                                            _lib.int32_array(bits[:-1]), len(bits) - 1, bits[-1],
+                                            None if src.norm is None else src.norm.data_ptr(), _lib.stream_ptr()))
+        return State(dst)
+
     # -- measurement -----------------------------------------------------------------------------------------
     def marginal_probabilities(self, qubit_indices):
         """float64 marginal distribution of the listed qubits (first = most significant bit of the outcome): the

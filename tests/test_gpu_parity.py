@@ -548,3 +548,82 @@ def test_full_size_properties(dtype, n):
     # measurement at full size: outcome is consistent with the marginals and collapses the state
     bits = a.measure(qi, u=0.5)
     assert a.marginal_probabilities(qi)[int(''.join(map(str, bits)), 2)] > 1 - tol
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_u_f_is_applied_as_an_index_permutation(dtype):
+    """U_f(state) through the permutation kernel (qcs_apply_uf) == the oracle applying the full permutation matrix;
+    the operator tensor is not built on that path, and everything that needs the tensor still gets the reference's."""
+    rng = np.random.default_rng(90)
+    for d, n in ((2, 2), (2, 7), (3, 9), (5, 5), (6, 13), (9, 14), (11, 11)):
+        table = rng.integers(0, 2, size=2 ** (d - 1))
+        f = lambda *bits, table=table: int(table[int(''.join(map(str, bits)), 2)])
+        op = qc.U_f(f, d)
+        vec = rand_state_vec(rng, n)
+        s = _state(vec, dtype)
+        qi = [int(q) for q in rng.permutation(n)[:d]]
+        got = op(s, qubit_indices=qi)
+        assert op._tensor is None                      # the 2^(2d) tensor was never materialised
+        cols = np.arange(2 ** d)
+        M = np.zeros((2 ** d, 2 ** d))
+        M[(cols & ~1) | ((cols & 1) ^ table[cols >> 1]), cols] = 1
+        want = oracle_apply(M, vec, qi)
+        check_close(got.to_column_vector(), want, dtype, 'test_u_f_is_applied_as_an_index_permutation')
+        check_close(s.to_column_vector(), vec, dtype, 'test_u_f_is_applied_as_an_index_permutation')   # argument untouched
+    # a lazily scaled (non-unit buffer) argument, then the tensor paths: composition and density operators
+    op = qc.U_f(lambda a, b: a ^ b, 3)
+    s = qc.Operator.from_matrix(np.array([[2.0, 0], [0, 0.5]]))(_state(rand_state_vec(rng, 4), dtype), qubit_indices=[1])
+    want = oracle_apply(op.to_matrix(), s.to_column_vector(), [3, 0, 2])
+    check_close(op(s, qubit_indices=[3, 0, 2]).to_column_vector(), want, dtype, 'test_u_f_is_applied_as_an_index_permutation')
+    comp = qc.Hadamard(3)(qc.U_f(lambda a, b: a & b, 3))
+    assert np.max(np.abs(comp.to_matrix() - qc.Hadamard(3).to_matrix() @ qc.U_f(lambda a, b: a & b, 3).to_matrix())) < 1e-14
+    rho = _state(rand_state_vec(rng, 3), dtype).density_operator()
+    out = qc.U_f(lambda a, b: a | b, 3)(rho)
+    U = qc.U_f(lambda a, b: a | b, 3).to_matrix()
+    want_rho = U @ rho.to_matrix() @ U.conj().T
+    assert np.max(np.abs(out.to_matrix() - want_rho)) < TOL[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_operator_relabelled_after_use_is_reanalysed(dtype):
+    """apply, swap_qubits / permute_qubits (in place, reference operators.py:125-170), apply again: the second
+    application must see the new tensor, not a cached plan or device matrix"""
+    rng = np.random.default_rng(91)
+    n = 9
+    vec = rand_state_vec(rng, n)
+    s = _state(vec, dtype)
+    op = qc.CNOT()
+    check_close(op(s, qubit_indices=[2, 5]).to_column_vector(), oracle_apply(op.to_matrix(), vec, [2, 5]), dtype, 'relabel')
+    op.swap_qubits(0, 1)
+    check_close(op(s, qubit_indices=[2, 5]).to_column_vector(), oracle_apply(op.to_matrix(), vec, [2, 5]), dtype, 'relabel')
+    big = qc.Operator.from_matrix(rand_unitary(rng, 6))
+    qi = [0, 8, 3, 4, 1, 6]
+    check_close(big(s, qubit_indices=qi).to_column_vector(), oracle_apply(big.to_matrix(), vec, qi), dtype, 'relabel')
+    big.permute_qubits([5, 3, 0, 1, 2, 4])
+    check_close(big(s, qubit_indices=qi).to_column_vector(), oracle_apply(big.to_matrix(), vec, qi), dtype, 'relabel')
+
+
+def test_ensemble_of_mixed_amplitude_types_is_rejected():
+    a = qc.zeros(3, dtype=np.complex64)
+    b = qc.zeros(3, dtype=np.complex128)
+    with pytest.raises(TypeError):
+        qc.DensityOperator.from_ensemble([a, b], [0.5, 0.5])
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_circuit_whose_pass_ends_in_a_dense_gate(dtype):
+    """advisor repro: H, RX, then a 3-qubit unitary / U_f last in its pass -- program order must survive scheduling"""
+    from qcircuits_b200.circuit import Circuit
+    rng = np.random.default_rng(92)
+    n = 12
+    for last in (qc.Operator.from_matrix(rand_unitary(rng, 3)), qc.U_f(lambda a, b: a ^ b, 3)):
+        c = Circuit(n)
+        c.append(qc.Hadamard(), [0])
+        c.append(qc.RotationX(0.3), [1])
+        c.append(last, [0, 1, 2])
+        vec = rand_state_vec(rng, n)
+        want = vec
+        for g in c.gates:
+            want = orc.apply_matrix_flat(g.plan.full, want, g.bits, renorm=False)
+        got = c.run(_state(vec, dtype)).to_column_vector()
+        check_close(got, want / np.linalg.norm(want), dtype, 'test_circuit_whose_pass_ends_in_a_dense_gate')
