@@ -268,7 +268,6 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     const int L = P.L;
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(MT);
     const uint32_t svec_tid = Layout::vec((uint32_t)gtid);
-    const uint32_t svec_step = Layout::vec((uint32_t)NT);
     const int scale_mode = P.scale_mode;
     float fr = 1.0f, fi = 0.0f;
     if (scale_mode) {
@@ -290,12 +289,11 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
 
     auto issue_load = [&](uint64_t it, int st) {
         const uint64_t base = tile_base_of(vcta + it * vgrid, P);
-        uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
+        const uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
             const uint4 *gp = src + ((base + hi_off[k]) >> VSHIFT);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
-            sp += svec_step * 16u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp + Layout::vec((uint32_t)(k * NT)) * 16u), "l"(gp) : "memory");
         }
     };
     if (my_tiles > 0) issue_load(0, 0);
@@ -321,7 +319,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         const uint4 *sbase = reinterpret_cast<const uint4 *>(stage) + svec_tid;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            uint4 val = sbase[k * svec_step];
+            uint4 val = sbase[Layout::vec((uint32_t)(k * NT))];
             if (scale_mode == 1) val = vec_scale<float>(val, fr);
             else if (scale_mode == 2) val = vec_cscale<float>(val, fr, fi);
             vec_norm_acc(tacc, val, 0.0f);

@@ -27,17 +27,24 @@ namespace qcs {
 // ------------------------------------------------------------------------------------------------
 // shared-memory layouts (indices in units of one amplitude / one 16-byte vector)
 // ------------------------------------------------------------------------------------------------
-// Padded: one 16-byte pad after every 128-byte row.  A thread that owns 2^r consecutive amplitudes
-// (register bits = low bits) then strides 144 bytes between lanes instead of 128: conflict-free for
-// 128-bit accesses.  Both maps are additive over disjoint bit sets (no carries), which the sweep uses.
+// Padded: one 16-byte pad after every 128-byte row, one more after every 8 rows and one more after every 64 rows.
+// Tile bit b then moves an amplitude by 8 * 2^b bytes plus pads whose sum is 16, 32 or 64 (mod 128) for EVERY b >= 4
+// (complex64; b >= 3 for complex128), cycling with period three: any three consecutive tile bits that land on the lanes
+// of a quarter warp address eight different 16-byte slots of a 128-byte bank row -- conflict-free 128-bit accesses
+// whichever bits a sweep keeps in registers.  (With the single-level pad of round 1 every bit above 6 moved a lane by a
+// multiple of 128 bytes: 23 % of the shared-memory wavefronts of a tensor-core pass were conflict replays.)
+// All maps are additive over disjoint bit sets (no carries), which the sweeps and the staging loops use.
 template <typename C> struct PaddedLayout {
     static constexpr int ROW = 128 / sizeof(C);                 // amplitudes per row
     static constexpr int PADA = 16 / sizeof(C);                 // pad, in amplitudes
-    static __host__ __device__ __forceinline__ uint32_t amp(uint32_t i) { return i + (i / ROW) * PADA; }
-    static __host__ __device__ __forceinline__ uint32_t vec(uint32_t v) { return v + (v >> 3); }
+    static __host__ __device__ __forceinline__ constexpr uint32_t amp(uint32_t i) {
+        return i + ((i / ROW) + (i / (8 * ROW)) + (i / (64 * ROW))) * PADA;
+    }
+    static __host__ __device__ __forceinline__ constexpr uint32_t vec(uint32_t v) { return v + (v >> 3) + (v >> 6) + (v >> 9); }
     static __host__ __device__ __forceinline__ size_t bytes(int m) {
         const size_t raw = sizeof(C) << m;
-        return raw + ((raw + 127) / 128) * 16;
+        const size_t rows = (raw + 127) / 128;
+        return raw + (rows + (rows + 7) / 8 + (rows + 63) / 64) * 16;
     }
 };
 template <typename C> struct LinearLayout {
@@ -469,11 +476,9 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(m);
     const uint32_t nchunks = 1u << (m - L);
     const uint32_t chunk_vecs = (1u << L) >> VSHIFT;     // 16-byte vectors per contiguous chunk
-    const uint32_t chunk_svecs = Layout::vec(chunk_vecs);// ... and their padded extent in shared memory
     // this thread's vectors: v = tid, tid + nt, ... ; the padded map is additive over the disjoint bit
     // ranges of tid and the stride, so the shared-memory address advances by a constant
     const uint32_t svec_tid = Layout::vec((uint32_t)tid);
-    const uint32_t svec_step = Layout::vec((uint32_t)nt);
     const int scale_mode = P.scale_mode;                 // 0 none, 1 real, 2 complex
     R fr = R(1), fi = R(0);
     if (scale_mode) {
@@ -507,18 +512,17 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
                 const uint4 *gp = src + ((base + hi_off[k]) >> VSHIFT);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
-                sp += svec_step * 16u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp + Layout::vec((uint32_t)(k * NT)) * 16u), "l"(gp)
+                             : "memory");
             }
         } else {
             for (uint32_t c = 0; c < nchunks; ++c) {
                 const uint4 *gp = src + ((base + chunk_off[c]) >> VSHIFT);
-                uint32_t sp = stage_u32 + c * chunk_svecs * 16u;
+                const uint32_t sp = stage_u32 + Layout::vec(c * chunk_vecs) * 16u;
                 for (uint32_t w = 0; w < chunk_vecs; w += nt) {
                     if (w + tid < chunk_vecs)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(gp) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp + Layout::vec(w) * 16u), "l"(gp) : "memory");
                     gp += nt;
-                    sp += svec_step * 16u;
                 }
             }
         }
@@ -551,15 +555,14 @@ __global__ void __launch_bounds__((PipeThreads<R, MT>::value), OCC) tile_kernel_
         };
         if (FAST) {
 #pragma unroll
-            for (int k = 0; k < NK; ++k) emit(sbase + k * svec_step, dst + ((base + hi_off[k]) >> VSHIFT));
+            for (int k = 0; k < NK; ++k) emit(sbase + Layout::vec((uint32_t)(k * NT)), dst + ((base + hi_off[k]) >> VSHIFT));
         } else {
             for (uint32_t c = 0; c < nchunks; ++c) {
                 uint4 *gp = dst + ((base + chunk_off[c]) >> VSHIFT);
-                const uint4 *sp = sbase + c * chunk_svecs;
+                const uint4 *sp = sbase + Layout::vec(c * chunk_vecs);
                 for (uint32_t w = 0; w < chunk_vecs; w += nt) {
-                    if (w + tid < chunk_vecs) emit(sp, gp);
+                    if (w + tid < chunk_vecs) emit(sp + Layout::vec(w), gp);
                     gp += nt;
-                    sp += svec_step;
                 }
             }
         }
@@ -1530,9 +1533,10 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         if (rc != QCS_OK) return rc;
         P.tc_mats = reinterpret_cast<const unsigned char *>(ws) + WS_TC_OFFSET;
         return launch_tc(P, dev, stream);
+    } else {
+        const int mode = tile_mode();
+        return c64 ? launch_tile<float, Prog>(P, dev, mode, stream) : launch_tile<double, Prog>(P, dev, mode, stream);
     }
-    const int mode = tile_mode();
-    return c64 ? launch_tile<float, Prog>(P, dev, mode, stream) : launch_tile<double, Prog>(P, dev, mode, stream);
 }
 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,

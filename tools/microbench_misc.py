@@ -50,15 +50,18 @@ def main():
             s = qc.Hadamard()(s, qubit_indices=[q])
         dv = s._dv
         row(dtype, 'abs2 sum only (norm)', timeit(lambda: dv.norm2()), N * B)
-        row(dtype, 'dot', timeit(lambda: dv.dot(dv)), 2 * N * B)
+        other = dv.clone()                      # a DIFFERENT buffer: <a|a> on one buffer reads half the bytes from L2
+        row(dtype, 'dot (two distinct buffers)', timeit(lambda: dv.dot(other)), 2 * N * B)
+        del other
         row(dtype, 'scale (renormalize_)', timeit(lambda: dv.scaled(0.5)), 2 * N * B)
         for m, bits in ((1, [n - 1]), (3, [n - 1, 5, 0]), (8, list(range(n - 1, n - 9, -1))), (10, list(range(9, -1, -1))),
                         (16, list(range(2, 18)))):
             row(dtype, 'marginal_probs m=%d' % m, timeit(lambda: dv.marginals(bits)), N * B)
         row(dtype, 'collapse keep (1 qubit)', timeit(lambda: dv.collapsed([n - 1], 0, False)), 2 * N * B)
-        row(dtype, 'collapse remove (1 high qubit)', timeit(lambda: dv.collapsed([n - 1], 0, True)), N * B + N * B // 2)
-        row(dtype, 'collapse remove (1 low qubit)', timeit(lambda: dv.collapsed([0], 0, True)), N * B + N * B // 2)
-        row(dtype, 'collapse remove (3 qubits)', timeit(lambda: dv.collapsed([n - 1, 7, 0], 5, True)), N * B + N * B // 8)
+        # removal reads only the kept 1 / 2^m of the amplitudes and writes as many
+        row(dtype, 'collapse remove (1 high qubit)', timeit(lambda: dv.collapsed([n - 1], 0, True)), N * B // 2 + N * B // 2)
+        row(dtype, 'collapse remove (1 low qubit: every other amplitude)', timeit(lambda: dv.collapsed([0], 0, True)), N * B // 2 + N * B // 2)
+        row(dtype, 'collapse remove (3 qubits)', timeit(lambda: dv.collapsed([n - 1, 7, 0], 5, True)), N * B // 8 + N * B // 8)
         perm = list(range(n))
         perm[0], perm[n - 1] = perm[n - 1], perm[0]
         row(dtype, 'permute_bits (swap bit 0 <-> top)', timeit(lambda: dv.permuted(perm)), 2 * N * B)
@@ -73,9 +76,9 @@ def main():
         b = qc.Hadamard()(b, qubit_indices=[1])
         row(dtype, 'kron (n-4) x 4', timeit(lambda: a._dv.kron(b._dv)), N * B + N * B // 16)
         row(dtype, 'kron 4 x (n-4)', timeit(lambda: b._dv.kron(a._dv)), N * B + N * B // 16)
-        lc = a._dv
-        row(dtype, 'lincomb (State + State), n-4 qubits', timeit(lambda: lc.lincomb(lc, 1.0, 1.0)), 3 * (N // 16) * B)
-        del a, b, lc
+        lc, lc2 = a._dv, a._dv.clone()          # two distinct operands
+        row(dtype, 'lincomb (State + State, distinct operands), n-4 qubits', timeit(lambda: lc.lincomb(lc2, 1.0, 1.0)), 3 * (N // 16) * B)
+        del a, b, lc, lc2
         torch.cuda.empty_cache()
         # density operator helpers on d = n // 2 qubits (rank 2d tensor)
         d = (n - 2) // 2
