@@ -66,7 +66,14 @@ def test_permute_qubits_of_large_states(dtype):
         keep_last = [int(a) for a in rng.permutation(n - 1)] + [n - 1]       # flat bit 0 stays in place
         swap_ends = list(range(n))
         swap_ends[0], swap_ends[n - 1] = n - 1, 0
-        for axes in perms + [keep_last, swap_ends, list(range(n))]:
+        # flat bit 0 (the last qubit) traded with near and far bits: the 2 x 2 block form of the complex64 kernel
+        moved = []
+        for other in (n - 2, n - 3, n - 8, n - 11, n - 13, 1):
+            axes = list(range(n))
+            axes[n - 1], axes[other] = other, n - 1
+            moved.append(axes)
+        cyc = [n - 1] + list(range(n - 1))                                   # every bit moves up by one
+        for axes in perms + [keep_last, swap_ends, list(range(n)), cyc] + moved:
             s = _state(vec, dtype)
             s.permute_qubits(axes)
             assert rel_err(s._t, np.transpose(vec.reshape([2] * n), axes)) < tol, (n, axes)

@@ -49,6 +49,11 @@ def main():
         for q in (0, n // 2, n - 1):
             s = qc.Hadamard()(s, qubit_indices=[q])
         dv = s._dv
+        # references: what a write-only and a copy stream reach on this box (torch fill / copy of the same buffer)
+        scratch = torch.empty_like(dv.buf)
+        row(dtype, 'reference: write-only stream (torch zero_)', timeit(lambda: scratch.zero_()), N * B)
+        row(dtype, 'reference: copy stream (torch copy_)', timeit(lambda: scratch.copy_(dv.buf)), 2 * N * B)
+        del scratch
         row(dtype, 'abs2 sum only (norm)', timeit(lambda: dv.norm2()), N * B)
         other = dv.clone()                      # a DIFFERENT buffer: <a|a> on one buffer reads half the bytes from L2
         row(dtype, 'dot (two distinct buffers)', timeit(lambda: dv.dot(other)), 2 * N * B)
@@ -57,7 +62,8 @@ def main():
         for m, bits in ((1, [n - 1]), (3, [n - 1, 5, 0]), (8, list(range(n - 1, n - 9, -1))), (10, list(range(9, -1, -1))),
                         (16, list(range(2, 18)))):
             row(dtype, 'marginal_probs m=%d' % m, timeit(lambda: dv.marginals(bits)), N * B)
-        row(dtype, 'collapse keep (1 qubit)', timeit(lambda: dv.collapsed([n - 1], 0, False)), 2 * N * B)
+        # keeping reads the kept half and writes everything (zeros elsewhere)
+        row(dtype, 'collapse keep (1 qubit)', timeit(lambda: dv.collapsed([n - 1], 0, False)), N * B // 2 + N * B)
         # removal reads only the kept 1 / 2^m of the amplitudes and writes as many
         row(dtype, 'collapse remove (1 high qubit)', timeit(lambda: dv.collapsed([n - 1], 0, True)), N * B // 2 + N * B // 2)
         row(dtype, 'collapse remove (1 low qubit: every other amplitude)', timeit(lambda: dv.collapsed([0], 0, True)), N * B // 2 + N * B // 2)
@@ -65,6 +71,9 @@ def main():
         perm = list(range(n))
         perm[0], perm[n - 1] = perm[n - 1], perm[0]
         row(dtype, 'permute_bits (swap bit 0 <-> top)', timeit(lambda: dv.permuted(perm)), 2 * N * B)
+        perm3 = list(range(n))
+        perm3[0], perm3[7] = perm3[7], perm3[0]
+        row(dtype, 'permute_bits (swap bit 0 <-> bit 7)', timeit(lambda: dv.permuted(perm3)), 2 * N * B)
         perm2 = list(range(n))
         perm2[12], perm2[n - 1] = perm2[n - 1], perm2[12]
         row(dtype, 'permute_bits (swap bit 12 <-> top)', timeit(lambda: dv.permuted(perm2)), 2 * N * B)
