@@ -1,6 +1,7 @@
 // Internal declarations shared by the libqcs translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/qcs.h"
@@ -48,7 +49,7 @@ struct RegOp {                   // 16 bytes, read with one 128-bit shared-memor
 };
 struct OuterPred { uint64_t care, val; };   // flat-index bits outside the tile
 constexpr int SWEEP_REG = 0, SWEEP_GENERIC = 1;
-struct Sweep {
+struct alignas(8) Sweep {
     int32_t kind, first, count, nreg;
     int8_t rpos[REG_BITS_MAX];       // tile-local positions of the register bits, ascending
     int16_t thread_phase;            // some PHASE op of the sweep is uniform over a thread's amplitudes
@@ -58,6 +59,10 @@ struct Sweep {
     // group and is inserted at rank `hrank` among the 8 non-register tile bits (hrank = 7: plain register sweep)
     int16_t tc_slot;                 // -1: no tensor-core block in this sweep
     int16_t hrank;
+    // everything the tensor-core kernel needs of the record in ONE 8-byte word (one broadcast shared-memory load per
+    // thread and sweep instead of ~19 dependent ones): rpos[j] at bits 4j (j < 4), hrank at 16, tc_slot + 1 at 20,
+    // flags at 24 (1: has register ops, 2: dense2 interpreter, 4: thread phase), first register op at 32
+    uint64_t packed;                 // (8-byte aligned: read with one 64-bit shared-memory load)
     // host-precomputed addressing of the compile-time-geometry path: inserting a zero at rpos[j] is
     // x += x & himask[j]; stride[j] = padded shared-memory distance in bytes between the two values of bit j
     uint32_t himask[REG_BITS_MAX];
@@ -100,6 +105,7 @@ constexpr int TC_GROUP_THREADS = 256;                // two groups per CTA, each
 constexpr int TC_STAGES = 2;                         // ring stages per group
 constexpr int64_t WS_TC_OFFSET = 32768;              // block-matrix images live in the caller's workspace from here
 constexpr int TC_UPLOAD_RING = 8;                    // pinned host staging sets for their upload (one per launch in flight)
+static_assert(sizeof(Sweep) % 8 == 0 && offsetof(Sweep, packed) % 8 == 0, "Sweep::packed is read with one 64-bit load");
 static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes");
 
 struct DeviceInfo { int sms; size_t smem_per_sm; };

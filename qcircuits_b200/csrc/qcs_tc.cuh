@@ -131,16 +131,22 @@ template <typename Layout>
 __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp *rops, const float2 *pool, uint64_t outer_ok,
                                       Ctx &ctx) {
     constexpr int NX = 16;
-    const uint32_t rho = (uint32_t)ctx.gtid & 127u, h = (uint32_t)ctx.gtid >> 7, p = (uint32_t)sw.hrank;
+    // the record as one 8-byte broadcast load; masks and strides are recomputed from the four register-bit positions
+    // (a dozen integer ops) instead of being fetched with dependent shared-memory loads
+    uint32_t plo, phi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(plo), "=r"(phi) : "r"(smem_u32(&sw.packed)) : "memory");
+    const uint32_t rho = (uint32_t)ctx.gtid & 127u, h = (uint32_t)ctx.gtid >> 7, p = (plo >> 16) & 15u;
+    const uint32_t flags = plo >> 24, first = phi;
+    const int tc_slot = (int)((plo >> 20) & 15u) - 1;
     uint32_t base = ((rho >> p) << (p + 1)) | (h << p) | (rho & ((1u << p) - 1u));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) base += base & sw.himask[j];
-    const bool VEC = sw.rpos[0] == 0;
+    for (int j = 0; j < 4; ++j) base += base & (0xFFFFFFFFu << ((plo >> (4 * j)) & 15u));
+    const bool VEC = (plo & 15u) == 0;
     uint32_t addr[NX];
     addr[0] = smem_u32(tile) + Layout::amp(base) * (uint32_t)sizeof(float2);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t st = sw.stride[j];
+        const uint32_t st = Layout::amp(1u << ((plo >> (4 * j)) & 15u)) * (uint32_t)sizeof(float2);
 #pragma unroll
         for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st;
     }
@@ -155,16 +161,16 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
         for (int x = 0; x < NX; ++x)
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[x].x), "=f"(a[x].y) : "r"(addr[x]) : "memory");
     }
-    if (sw.count > 0) {
+    if (flags & 1u) {
         float2 ph = make_float2(1.0f, 0.0f);
-        if (sw.has_dense2) run_sweep_ops_dense2(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
-        else run_sweep_ops(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
-        if (sw.thread_phase) {
+        if (flags & 2u) run_sweep_ops_dense2(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
+        else run_sweep_ops(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
+        if (flags & 4u) {
 #pragma unroll
             for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
         }
     }
-    if (sw.tc_slot >= 0) {
+    if (tc_slot >= 0) {
         const uint32_t col = ctx.lane_addr + 16u * h;
         {
             uint32_t hi[NX], lo[NX];
@@ -191,7 +197,7 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
             // (a spinning try_wait loop in every warp took issue slots from the other group's register work)
             fence_after();
             if (elect_one()) {
-                issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)sw.tc_slot * (uint32_t)TC_SLOT_BYTES);
+                issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)tc_slot * (uint32_t)TC_SLOT_BYTES);
                 commit(ctx.bar);
             }
             __syncwarp();
@@ -239,7 +245,14 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     ProgView pv;
     const uint64_t *chunk_off;
     const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, 2 * NT);
-    const uint64_t *hi_off = chunk_off + (1u << P.H);
+    // flat offsets of the top three tile bits, in registers (in vector units): vector k of a thread sits at the OR of those
+    // whose bit of k is set -- no table look-ups in the load and store loops
+    uint64_t top_off[3];
+    for (int j = 0; j < 3; ++j) {
+        const int i = TILE_MIN_BITS_C64 - 3 + j;
+        top_off[j] = (1ull << (i < P.L ? i : P.hbits[i - P.L])) >> 1;
+    }
+    (void)chunk_off;
     // block-matrix images
     unsigned char *bimg = smem_all + prog_bytes;
     {
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         const uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            const uint4 *gp = src + ((base + hi_off[k]) >> VSHIFT);
+            const uint4 *gp = src + ((base >> VSHIFT) + ((k & 1) ? top_off[0] : 0ull) + ((k & 2) ? top_off[1] : 0ull) + ((k & 4) ? top_off[2] : 0ull));
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp + Layout::vec((uint32_t)(k * NT)) * 16u), "l"(gp) : "memory");
         }
     };
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
             if (scale_mode == 1) val = vec_scale<float>(val, fr);
             else if (scale_mode == 2) val = vec_cscale<float>(val, fr, fi);
             vec_norm_acc(tacc, val, 0.0f);
-            dst[(base + hi_off[k]) >> VSHIFT] = val;
+            dst[(base >> VSHIFT) + ((k & 1) ? top_off[0] : 0ull) + ((k & 2) ? top_off[1] : 0ull) + ((k & 4) ? top_off[2] : 0ull)] = val;
         }
         nacc[0] += (double)tacc;
         st ^= 1;

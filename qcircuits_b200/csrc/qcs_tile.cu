@@ -140,16 +140,21 @@ __device__ __forceinline__ void reg_sweep_fast(typename CxT<R>::T *tile, const S
                                                const typename CxT<R>::T *pool, uint64_t outer_ok, int tid) {
     using C = typename CxT<R>::T;
     constexpr int NX = 1 << RB;
-    const bool VEC = sizeof(C) == 8 && sw.rpos[0] == 0;     // complex64 pairs move as one 128-bit access
+    // the record as one 8-byte broadcast load (Sweep::packed); masks and strides are recomputed from the register-bit
+    // positions instead of being fetched with dependent shared-memory loads
+    uint32_t plo, phi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(plo), "=r"(phi) : "r"(smem_u32(&sw.packed)) : "memory");
+    const uint32_t flags = plo >> 24, first = phi;
+    const bool VEC = sizeof(C) == 8 && (plo & 15u) == 0;     // complex64 pairs move as one 128-bit access
     uint32_t base = (uint32_t)tid;
 #pragma unroll
-    for (int j = 0; j < RB; ++j) base += base & sw.himask[j];
+    for (int j = 0; j < RB; ++j) base += base & (0xFFFFFFFFu << ((plo >> (4 * j)) & 15u));
     const uint32_t tile_u32 = smem_u32(tile) + Layout::amp(base) * (uint32_t)sizeof(C);
     uint32_t addr[NX];
     addr[0] = tile_u32;
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
-        const uint32_t st = sw.stride[j];
+        const uint32_t st = Layout::amp(1u << ((plo >> (4 * j)) & 15u)) * (uint32_t)sizeof(C);
 #pragma unroll
         for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st;
     }
@@ -167,9 +172,9 @@ __device__ __forceinline__ void reg_sweep_fast(typename CxT<R>::T *tile, const S
         for (int x = 0; x < NX; ++x) a[x] = *reinterpret_cast<const C *>(__cvta_shared_to_generic(addr[x]));
     }
     C ph = cx<R>(R(1), R(0));     // product of the phases that are uniform over this thread's amplitudes
-    if (sw.has_dense2) run_sweep_ops_dense2(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
-    else run_sweep_ops(a, ph, smem_u32(rops + sw.first), smem_u32(pool), base, outer_ok);
-    if (sw.thread_phase) {
+    if (flags & 2u) run_sweep_ops_dense2(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
+    else run_sweep_ops(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
+    if (flags & 4u) {
 #pragma unroll
         for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
     }
@@ -1468,6 +1473,12 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                     ++sw.count;
                 }
             }
+        }
+        {
+            const uint32_t lo = (uint32_t)sw.rpos[0] | ((uint32_t)sw.rpos[1] << 4) | ((uint32_t)sw.rpos[2] << 8) |
+                                ((uint32_t)sw.rpos[3] << 12) | ((uint32_t)sw.hrank << 16) | ((uint32_t)(sw.tc_slot + 1) << 20) |
+                                ((sw.count > 0 ? 1u : 0u) | (sw.has_dense2 ? 2u : 0u) | (sw.thread_phase ? 4u : 0u)) << 24;
+            sw.packed = (uint64_t)lo | ((uint64_t)(uint32_t)sw.first << 32);
         }
         if (sw.count > 0 || tc_sweep) {    // (a run of exact identities produces no work)
             if (P.nregops >= Prog::MAX_REGOPS) return set_error(QCS_ERR_UNSUPPORTED, "too many register ops");
