@@ -351,6 +351,23 @@ def main():
         del rho
         torch.cuda.empty_cache()
 
+    # how the passes run, and what the tensor-core blocks amount to: a block applies 36 tcgen05.mma per 128-row tile
+    # (12 x M128 N64 K8 + 24 x M128 N32 K8, the 3-term TF32 split) = 3.15 MFLOP per tile of 2^12 amplitudes
+    plan = circ.plan_summary(np_dtype, fuse=fuse, max_ops=args.max_ops)
+    tensor = None
+    if plan['blocks']:
+        flop = plan['blocks'] * (2.0 ** n / 4096.0) * (12 * 128 * 64 * 8 * 2 + 24 * 128 * 32 * 8 * 2)
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                tf32_peak = float(json.load(f)['bf16_tflops_sustained']) / 2.0
+            tf32_src = 'MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)'
+        except Exception:
+            tf32_peak, tf32_src = 700.0, 'B200_PROFILING.md fallback 1.4 PFLOP/s sustained bf16 / 2'
+        tensor = {'tf32_tflops_achieved_over_the_step': flop / (ms_per_step * 1e-3) / 1e12, 'tf32_peak_tflops': tf32_peak,
+                  'frac': flop / (ms_per_step * 1e-3) / 1e12 / tf32_peak, 'peak_source': tf32_src,
+                  'note': 'executed TF32 flops (3 terms) of the dense blocks / step time; the pass is bound by the shared-memory '
+                          'pipe, not the tensor pipe (DESIGN.md 3.1b)'}
+
     line = {
         'metric': 'gates/s, random layered circuit', 'value': value, 'unit': 'gates/s', 'n_gpus': 1,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -363,9 +380,14 @@ def main():
                    'l2': 'state (%.1f GiB) is far larger than L2; no flush needed' % (2 ** n * amp_bytes / 2 ** 30),
                    'plan_s': plan_s},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': recorded_traffic('tile_%s_%dq' % (args.dtype, n)), 'peak_source': peak_src,
-                     'kernel': 'qcs::tile_kernel (fused gate pass)', 'bytes_per_launch': pass_bytes,
-                     'ms_per_launch': ms_per_step / passes, 'frac_of_8TBs_nominal': achieved / 8000.0},
+                     'traffic': recorded_traffic('tile_%s_%dq' % (args.dtype, n)),
+                     'traffic_source': 'profiles/traffic.json: dram__bytes read + written per launch of the committed ncu --set full '
+                                       'capture of the same kernel (a recorded constant, not measured in this run)',
+                     'peak_source': peak_src,
+                     'kernel': ('qcs::tile_kernel_tc (fused gate pass: dense 2^5 blocks on tcgen05 + register ops)'
+                                if plan['tensor_core_passes'] else 'qcs::tile_kernel_pipe (fused gate pass, register sweeps)'),
+                     'bytes_per_launch': pass_bytes, 'ms_per_launch': ms_per_step / passes,
+                     'frac_of_8TBs_nominal': achieved / 8000.0, 'plan': plan, 'tensor_pipe': tensor},
         'roofline_per_gate_pass': per_gate,
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': passes * args.steps,
         'amp_updates_per_s_per_gpu': ngates * 2.0 ** n / (ms_per_step * 1e-3),

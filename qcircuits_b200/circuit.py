@@ -412,3 +412,24 @@ class Circuit:
     def stats(self, dtype=np.complex128, fuse=True, max_ops=128):
         """(number of passes, number of gates) for the schedule used by run()."""
         return len(self._compiled(dtype, fuse, max_ops)), len(self.gates)
+
+    def plan_summary(self, dtype=np.complex128, fuse=True, max_ops=128):
+        """How the engine will run the compiled passes (qcs_plan_stats, no device needed): passes, passes on the
+        tensor-core kernel, sweeps, tensor-core blocks, gates inside blocks, register ops."""
+        lib = _lib.load()
+        stats = (ctypes.c_int32 * 128)()
+        out = {'passes': 0, 'tensor_core_passes': 0, 'sweeps': 0, 'blocks': 0, 'gates_in_blocks': 0, 'register_ops': 0,
+               'dense_passes': 0}
+        for item in self._compiled(dtype, fuse, max_ops):
+            out['passes'] += 1
+            if item[0] != 'tile':
+                out['dense_passes'] += 1
+                continue
+            _lib.check(lib.qcs_plan_stats(self.n, _lib.dtype_code(dtype), item[1], len(item[1]), stats))
+            nb = stats[7] & 255
+            out['tensor_core_passes'] += 1 if nb else 0
+            out['sweeps'] += stats[1]
+            out['blocks'] += nb
+            out['gates_in_blocks'] += stats[7] >> 8
+            out['register_ops'] += stats[2] - stats[1]
+        return out
