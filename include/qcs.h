@@ -142,6 +142,13 @@ int qcs_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype,
 int qcs_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t *src_bit,
                      qcs_stream stream);
 
+/* OperatorBase.adj (operators.py:95-114: np.conj + transpose of every (out, in) axis pair) and the conjugated matrix of
+ * U rho U^dagger (operators.py:317-321), for operator tensors that live on the device:
+ * dst[i] = conj(src[j]) with the same index map as qcs_permute_bits.  The adjoint of a d-qubit operator tensor
+ * (2d flat bits, out-wire of qubit q on bit 2(d-1-q)+1) is src_bit[b] = b ^ 1. */
+int qcs_conj_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t *src_bit,
+                          qcs_stream stream);
+
 /* U_f applied to a State (operators.py:809-853 builds the 2^d x 2^d permutation tensor with a Python loop and contracts
  * it with np.tensordot, :261): dst[i] = src[i XOR (f(x(i)) << tbit)] / sqrt(*norm_in), where x(i) gathers the flat bits
  * xbits[0..nx-1] of i (xbits[0] = most significant bit of x) and f is a packed truth table on the device (bit x of

@@ -148,11 +148,12 @@ class DeviceVector:
                                    _lib.stream_ptr()))
         return dst
 
-    def permuted(self, src_bit):
-        """dst[i] = src[j] with bit src_bit[b] of j = bit b of i."""
+    def permuted(self, src_bit, conj=False):
+        """dst[i] = src[j] (conj: its complex conjugate) with bit src_bit[b] of j = bit b of i."""
         dst = self._new_like()
-        check(_lib.load().qcs_permute_bits(dst.buf.data_ptr(), self.buf.data_ptr(), self.nbits, self.code,
-                                           _lib.int32_array(src_bit), _lib.stream_ptr()))
+        fn = _lib.load().qcs_conj_permute_bits if conj else _lib.load().qcs_permute_bits
+        check(fn(dst.buf.data_ptr(), self.buf.data_ptr(), self.nbits, self.code, _lib.int32_array(src_bit),
+                 _lib.stream_ptr()))
         dst.norm = self.norm
         return dst
 

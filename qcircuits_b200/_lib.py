@@ -15,7 +15,7 @@ QCS_MAX_OP_QUBITS = 4
 QCS_MAX_OPS = 128
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libqcs.so')
+LIB_PATH = os.environ.get('QCS_LIB') or os.path.join(_HERE, 'libqcs.so')     # (QCS_LIB: planner experiments)
 
 c_void_p, c_int, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -55,6 +55,7 @@ PROTOTYPES = {
     'qcs_kron': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p]),
     'qcs_permute_bits': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'qcs_conj_permute_bits': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'qcs_set_basis': (c_int, [c_void_p, c_int, c_int, ctypes.c_uint64, c_void_p]),
     'qcs_marginal_probs': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                    ctypes.c_int64, c_void_p]),

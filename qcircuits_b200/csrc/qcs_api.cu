@@ -186,7 +186,15 @@ int qcs_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t
     if (int e = check_state(src, n, dtype)) return e;
     if (!src_bit) return set_error(QCS_ERR_ARG, "null permutation");
     if (dst == src) return set_error(QCS_ERR_ARG, "permute_bits cannot run in place");
-    return misc_permute(dst, src, n, dtype, src_bit, (cudaStream_t)stream);
+    return misc_permute(dst, src, n, dtype, src_bit, false, (cudaStream_t)stream);
+}
+
+int qcs_conj_permute_bits(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, qcs_stream stream) {
+    if (int e = check_state(dst, n, dtype)) return e;
+    if (int e = check_state(src, n, dtype)) return e;
+    if (!src_bit) return set_error(QCS_ERR_ARG, "null permutation");
+    if (dst == src) return set_error(QCS_ERR_ARG, "conj_permute_bits cannot run in place");
+    return misc_permute(dst, src, n, dtype, src_bit, true, (cudaStream_t)stream);
 }
 
 int qcs_apply_uf(void *dst, const void *src, int n, int dtype, const uint32_t *dev_table, const int32_t *xbits, int nx,

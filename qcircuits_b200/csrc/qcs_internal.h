@@ -130,7 +130,7 @@ int misc_lincomb(void *dst, const void *a, const void *b, int n, int dtype, cons
                  const double *norm_a, const double *norm_b, double *norm_out, void *ws, cudaStream_t st);
 int misc_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype, const double *norm_a,
               const double *norm_b, double *norm_out, void *ws, cudaStream_t st);
-int misc_permute(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, cudaStream_t st);
+int misc_permute(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, bool conj, cudaStream_t st);
 int misc_marginal(double *out, const void *src, int n, int dtype, const int32_t *bitpos, int m, const double *norm_in,
                   void *ws, int64_t ws_bytes, cudaStream_t st);
 int misc_collapse(void *dst, const void *src, int n, int dtype, const int32_t *bitpos, int m, uint64_t outcome,

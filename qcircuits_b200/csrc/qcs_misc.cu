@@ -249,21 +249,31 @@ __global__ void __launch_bounds__(EW_THREADS) kron_small_a_kernel(typename CxT<R
 }
 
 // ---- permute_bits (state.py:117,162) --------------------------------------------------------------
-template <typename C>
+// conjugation for the adjoint / conjugate forms of the bit permutation (operators.py:95-114): a sign flip of the
+// imaginary parts, on typed amplitudes and on raw 16-byte vectors (complex64: two amplitudes, complex128: one)
+template <bool CONJ, typename C> __device__ __forceinline__ C maybe_conj(C v) { if (CONJ) v.y = -v.y; return v; }
+template <bool CONJ, typename C> __device__ __forceinline__ uint4 maybe_conj_vec(uint4 v) {
+    if (CONJ) {
+        if (sizeof(C) == 8) { v.y ^= 0x80000000u; v.w ^= 0x80000000u; }
+        else v.w ^= 0x80000000u;
+    }
+    return v;
+}
+template <typename C, bool CONJ>
 __global__ void __launch_bounds__(EW_THREADS) permute_kernel(C *__restrict__ dst, const C *__restrict__ src, int n,
                                                              const __grid_constant__ BitList bl) {
     const uint64_t N = 1ull << n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t j = 0;
         for (int b = 0; b < n; ++b) j |= ((i >> b) & 1ull) << bl.pos[b];
-        dst[i] = src[j];
+        dst[i] = maybe_conj<CONJ>(src[j]);
     }
 }
 // Large states: the source index of destination element e = ((seg * 8 + j) * 256 + tid) * VE + u is an OR of
 // per-bit contributions, P(e) = Ps(seg) | Pj(j) | Pt(tid, u), so the n-step bit loop runs once per segment
 // instead of once per amplitude; the destination is written with 16-byte vectors, the source is read with
 // 16-byte vectors when flat bit 0 stays in place (complex64) and with 8-byte gathers otherwise.
-template <typename C>
+template <typename C, bool CONJ>
 __global__ void __launch_bounds__(EW_THREADS) permute_stream_kernel(C *__restrict__ dst, const C *__restrict__ src,
                                                                    const __grid_constant__ BinMap pm) {
     constexpr int VE = VecOf<C>::VE, LV = VecOf<C>::LV;
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(EW_THREADS) permute_stream_kernel(C *__restric
             }
         }
 #pragma unroll
-        for (int j = 0; j < MS_VECS; ++j) __stcs(vd + j * EW_THREADS, val[j]);
+        for (int j = 0; j < MS_VECS; ++j) __stcs(vd + j * EW_THREADS, maybe_conj_vec<CONJ, C>(val[j]));
     }
 }
 
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(EW_THREADS) permute_stream_kernel(C *__restric
 // takes the 2 x 2 block instead: destination pairs at i and i | 2^d0 (d0 = where source bit 0 goes) <- source pairs at
 // e and e | 2^j, transposed in registers; every access is a full 16-byte (complex64) or 32-byte (complex128) unit.
 // q enumerates the blocks: bit k of q is destination bit k + 1 (k + 1 < d0) or k + 2.
-template <typename C>
+template <typename C, bool CONJ>
 __global__ void __launch_bounds__(EW_THREADS) permute_quad_kernel(C *__restrict__ dst, const C *__restrict__ src,
                                                                   const __grid_constant__ BinMap pm, int d0) {
     constexpr int NVQ = sizeof(C) == 8 ? MS_VECS : MS_VECS / 2;     // blocks per thread and segment (same bytes in flight)
@@ -340,6 +350,7 @@ __global__ void __launch_bounds__(EW_THREADS) permute_quad_kernel(C *__restrict_
         }
 #pragma unroll
         for (int j = 0; j < NVQ; ++j) {
+            if (CONJ) { a0[j].y = -a0[j].y; a1[j].y = -a1[j].y; b0[j].y = -b0[j].y; b1[j].y = -b1[j].y; }
             const uint64_t q = (sgm << SEGB) | ((uint64_t)j << 8) | (uint64_t)tid;
             const uint64_t i = (((q >> (d0 - 1)) << d0) | (q & lowmask)) << 1;    // destination index, bits 0 and d0 clear
             if (sizeof(C) == 8) {
@@ -930,7 +941,8 @@ int misc_kron(void *dst, const void *a, int na, const void *b, int nb, int dtype
     return check_launch();
 }
 
-int misc_permute(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, cudaStream_t st) {
+template <bool CONJ>
+static int permute_impl(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, cudaStream_t st) {
     BitList bl;
     if (int e = make_bitlist(bl, src_bit, n, n, false)) return e;
     const uint64_t N = 1ull << n;
@@ -947,17 +959,21 @@ int misc_permute(void *dst, const void *src, int n, int dtype, const int32_t *sr
             uint64_t gridq = (uint64_t)device_info().sms * 8;
             const uint64_t nsegq = (N >> 2) >> (lv ? 11 : 10);
             if (gridq > nsegq) gridq = nsegq;
-            DISPATCH_C(dtype, (permute_quad_kernel<C><<<(unsigned)gridq, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, pm, d0)));
+            DISPATCH_C(dtype, (permute_quad_kernel<C, CONJ><<<(unsigned)gridq, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, pm, d0)));
             return check_launch();
         }
         uint64_t grid = (uint64_t)device_info().sms * 8;
         const uint64_t nseg = N >> (11 + lv);
         if (grid > nseg) grid = nseg;
-        DISPATCH_C(dtype, (permute_stream_kernel<C><<<(unsigned)grid, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, pm)));
+        DISPATCH_C(dtype, (permute_stream_kernel<C, CONJ><<<(unsigned)grid, EW_THREADS, 0, st>>>((C *)dst, (const C *)src, pm)));
         return check_launch();
     }
-    DISPATCH_C(dtype, (permute_kernel<C><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((C *)dst, (const C *)src, n, bl)));
+    DISPATCH_C(dtype, (permute_kernel<C, CONJ><<<ew_grid(N / 4 + 1), EW_THREADS, 0, st>>>((C *)dst, (const C *)src, n, bl)));
     return check_launch();
+}
+
+int misc_permute(void *dst, const void *src, int n, int dtype, const int32_t *src_bit, bool conj, cudaStream_t st) {
+    return conj ? permute_impl<true>(dst, src, n, dtype, src_bit, st) : permute_impl<false>(dst, src, n, dtype, src_bit, st);
 }
 
 template <typename T>

@@ -118,7 +118,15 @@ struct Ctx {
     uint64_t *bar;         // this group's completion barrier
     uint32_t phase;
     int group, gtid;
+#ifdef QCS_TC_DBG
+    uint32_t dbg;          // timing experiments only (scratch builds): 1 no MMA, 2 no split / tcgen05.st, 4 no tcgen05.ld, 8 no tile LDS / STS
+#endif
 };
+#ifdef QCS_TC_DBG
+#define TC_DBG(ctx, bit) ((ctx).dbg & (bit))
+#else
+#define TC_DBG(ctx, bit) false
+#endif
 
 // tf32 "hi" part: the 19 bits the tensor core reads (it ignores the low 13 mantissa bits); lo = x - hi is exact and
 // at most 2^-10 |x|, and ITS truncation to tf32 leaves 2^-20 |x| -- one AND + one subtraction per real number
@@ -143,6 +151,12 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
     for (int j = 0; j < 4; ++j) base += base & (0xFFFFFFFFu << ((plo >> (4 * j)) & 15u));
     const bool VEC = (plo & 15u) == 0;
     uint32_t addr[NX];
+    if (TC_DBG(ctx, 16u)) {      // (timing experiment: trivial conflict-free addresses, no layout arithmetic)
+#pragma unroll
+        for (int x = 0; x < NX; ++x)
+            addr[x] = smem_u32(tile) + (VEC ? (uint32_t)((x >> 1) * 256 + ctx.gtid) * 16u + (uint32_t)(x & 1) * 8u
+                                            : (uint32_t)(x * 256 + ctx.gtid) * 8u);
+    } else {
     addr[0] = smem_u32(tile) + Layout::amp(base) * (uint32_t)sizeof(float2);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -150,8 +164,12 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
 #pragma unroll
         for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st;
     }
+    }
     float2 a[NX];
-    if (VEC) {
+    if (TC_DBG(ctx, 8u)) {
+#pragma unroll
+        for (int x = 0; x < NX; ++x) a[x] = make_float2((float)x, (float)ctx.gtid);
+    } else if (VEC) {
 #pragma unroll
         for (int x = 0; x < NX; x += 2)
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -172,7 +190,7 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
     }
     if (tc_slot >= 0) {
         const uint32_t col = ctx.lane_addr + 16u * h;
-        {
+        if (!TC_DBG(ctx, 2u)) {
             uint32_t hi[NX], lo[NX];
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
@@ -197,16 +215,17 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
             // (a spinning try_wait loop in every warp took issue slots from the other group's register work)
             fence_after();
             if (elect_one()) {
-                issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)tc_slot * (uint32_t)TC_SLOT_BYTES);
+                if (!TC_DBG(ctx, 1u)) issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)tc_slot * (uint32_t)TC_SLOT_BYTES);
                 commit(ctx.bar);
             }
             __syncwarp();
             mbar_wait_bounded(ctx.bar, ctx.phase);
         }
         ctx.phase ^= 1u;
-        group_sync(ctx.group);
+        if (TC_DBG(ctx, 32u)) { if ((ctx.gtid >> 5) != 0) mbar_wait_bounded(ctx.bar, ctx.phase ^ 1u); }   // every warp watches the barrier itself
+        else group_sync(ctx.group);
         fence_after();
-        {
+        if (!TC_DBG(ctx, 4u)) {
             uint32_t re[NX], im[NX];
             ld16(col + COL_D, re);
             ld16(col + COL_D + 32u, im);
@@ -216,7 +235,9 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
         }
         fence_before();        // orders these tensor-memory reads before the next sweep's barrier + MMA
     }
-    if (VEC) {
+    if (TC_DBG(ctx, 8u)) {
+        if (a[3].x == 12345.678f) tile[0] = a[5];       // keep the values alive
+    } else if (VEC) {
 #pragma unroll
         for (int x = 0; x < NX; x += 2)
             asm volatile("st.shared.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(a[x].x), "f"(a[x].y), "f"(a[x + 1].x), "f"(a[x + 1].y),
@@ -277,6 +298,9 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     ctx.tbase = tmem_slot + 256u * (uint32_t)g;
     ctx.lane_addr = ctx.tbase + ((uint32_t)(((gtid >> 5) & 3) * 32) << 16);
     ctx.bimg0 = smem_u32(bimg);
+#ifdef QCS_TC_DBG
+    ctx.dbg = (uint32_t)P.tc_pad;
+#endif
 
     const int L = P.L;
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(MT);

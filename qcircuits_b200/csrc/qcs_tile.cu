@@ -1027,7 +1027,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         op_lmask[i] = local_mask(all & tile_mask);
         op_inside[i] = (all & ~tile_mask) == 0 && __builtin_popcountll(all) <= TC_BLOCK_BITS;
     }
-    P.n_tc = 0; P.tc_mats = nullptr; P.tc_pad = 0;
+    P.n_tc = 0; P.tc_mats = nullptr; P.tc_pad = tune_int("QCS_TC_DEBUG", 0);   // (read by scratch builds with -DQCS_TC_DBG only)
 
     // ---- matrix pool -----------------------------------------------------------------------------------
     const size_t csize = c64 ? 8 : 16;

@@ -58,6 +58,10 @@ class OperatorBase(Tensor):
     def adj(self):
         """Conjugate transpose: conjugate and swap every (out, in) axis pair (operators.py:95-114)."""
         r = self.rank
+        if isinstance(self, Operator) and r >= DEVICE_COMPOSE_MIN_BITS and _cuda_ready():
+            # large operators (SURVEY 8f rank 3): one conjugating bit permutation on the device, flat bit b <- b ^ 1;
+            # the result stays on the device until somebody reads its tensor
+            return Operator._from_device(self._device_tensor().permuted([b ^ 1 for b in range(r)], conj=True))
         swap_pairs = np.arange(r).reshape(r // 2, 2)[:, ::-1].reshape(-1)
         return self.__class__(np.conj(self._t).transpose(swap_pairs))
 
@@ -125,8 +129,13 @@ class Operator(OperatorBase):
     # ``_t`` is a property so that everything derived from the tensor -- the structure analysis of the matrix and
     # its device copies -- is dropped whenever the tensor changes: permute_qubits / swap_qubits rewrite it in place
     # (reference operators.py:125-170) and it may be assigned directly; the reference recomputes from _t on every call.
+    # Large operators (from 8 qubits up) that were produced on the device -- compositions, adjoints -- keep their tensor
+    # there (``_dev_tensor``, complex128) and download it only when somebody reads ``_t``.
     @property
     def _t(self):
+        if self._tensor is None:
+            dv = self._dev_tensor
+            self._tensor = dv.to_host().reshape([2] * dv.nbits)
         return self._tensor
 
     @_t.setter
@@ -134,6 +143,35 @@ class Operator(OperatorBase):
         self._tensor = value
         self._plan_cache = None       # structure analysis of the matrix (diagonal / controlled)
         self._dev_matrix = {}         # dtype -> device copy, for operators wider than 4 qubits
+        self._dev_tensor = None       # device copy of the tensor itself (large operators)
+
+    @classmethod
+    def _from_device(cls, dv):
+        """An Operator whose tensor lives on the device (``dv``: DeviceVector of 2d bits, complex128, no pending norm)."""
+        op = Operator.__new__(Operator)
+        op._tensor = None
+        op._plan_cache = None
+        op._dev_matrix = {}
+        op._dev_tensor = dv
+        return op
+
+    def _device_tensor(self):
+        """The tensor as a device vector of 2d flat bits (complex128), uploaded once and kept."""
+        if self._dev_tensor is None:
+            from ._device import DeviceVector
+            self._dev_tensor = DeviceVector.from_host(self._t, np.complex128)
+        return self._dev_tensor
+
+    @property
+    def _device_only(self):
+        """True while the tensor exists only on the device (nobody has read ``_t`` yet)."""
+        return self._tensor is None and getattr(self, '_dev_tensor', None) is not None
+
+    @property
+    def shape(self):
+        if self._device_only:
+            return (2,) * self._dev_tensor.nbits
+        return self._t.shape
 
     def __repr__(self):
         head = 'Operator('
@@ -188,7 +226,7 @@ class Operator(OperatorBase):
         complex128, no renormalisation (operators.py:275 renormalises states only)."""
         from ._device import DeviceVector, make_ops
         d = arg.rank // 2
-        dv = DeviceVector.from_host(arg._t, np.complex128)
+        dv = arg._device_tensor() if isinstance(arg, Operator) else DeviceVector.from_host(arg._t, np.complex128)
         bits = [2 * (d - 1 - q) + 1 for q in qi]
         plan = self._plan()
         if len(plan.targets) <= 4:
@@ -196,6 +234,8 @@ class Operator(OperatorBase):
             out = dv.apply_ops(ops, keep, track_norm=False)
         else:
             out = dv.apply_dense(self._device_matrix(np.complex128), plan.k, bits, track_norm=False)
+        if isinstance(arg, Operator):
+            return Operator._from_device(out)         # stays on the device; ``_t`` downloads on demand
         return arg.__class__(out.to_host().reshape([2] * (2 * d)))
 
     def _apply(self, arg, qubit_indices=None):
@@ -222,8 +262,16 @@ class Operator(OperatorBase):
         key = (np.dtype(dtype).str, conj, _lib.torch().cuda.current_device())
         dev = self._dev_matrix.get(key)
         if dev is None:
-            M = self._plan().full
-            dev = _lib.upload(np.conj(M) if conj else M, dtype)
+            if self._device_only and np.dtype(dtype) == np.complex128:
+                # device-resident tensor -> matrix (out wires, then in wires) without leaving the device
+                k = self.rank // 2
+                src_bit = [2 * b for b in range(k)] + [2 * b + 1 for b in range(k)]      # flat matrix bit <- tensor bit
+                dev = self._dev_tensor.permuted(src_bit, conj=conj).buf
+            else:
+                M = self._plan().full
+                if M is None:
+                    M = np.ascontiguousarray(self.to_matrix())
+                dev = _lib.upload(np.conj(M) if conj else M, dtype)
             self._dev_matrix[key] = dev
         return dev
 
@@ -233,8 +281,12 @@ class Operator(OperatorBase):
         a 2^k x 2^k matrix -- it was 2/3 of the run time of examples/grover_algorithm.py at d = 10) and only learn
         whether they are diagonal, in one pass."""
         if self._plan_cache is None:
-            M = np.ascontiguousarray(self.to_matrix())
             k = self.rank // 2
+            if k > _gates.ANALYZE_MAX_QUBITS and self._device_only:
+                # composed on the device: dense, and its matrix is made there too (_device_matrix)
+                self._plan_cache = _gates.GatePlan(k, [], list(range(k)), False, None, None)
+                return self._plan_cache
+            M = np.ascontiguousarray(self.to_matrix())
             if k > _gates.ANALYZE_MAX_QUBITS:
                 diag = np.diag(M)
                 if np.count_nonzero(M) == np.count_nonzero(diag):
@@ -372,6 +424,7 @@ class UfOperator(Operator):
         self._tensor = None
         self._plan_cache = None
         self._dev_matrix = {}
+        self._dev_tensor = None
 
     @property
     def _t(self):

@@ -147,6 +147,60 @@ def test_operator_composition_on_the_device():
     assert rel_err(B.to_matrix().reshape(-1), B.to_matrix().reshape(-1)) == 0
 
 
+def test_device_resident_operator_chain_and_adjoint():
+    """compositions and adjoints of large operators stay on the device (Operator._device_only) until
+    somebody reads the tensor; a chain A(B(C)).adj applied to a State never downloads.  Compared with the oracle's
+    restatement of operators.py:95-114 (adj) and :225-278 (composition), and with the matrix adjoint for both
+    amplitude types of the bit-permutation kernels (qcs_conj_permute_bits)."""
+    from qcircuits_b200 import operators as ops_mod
+    from qcircuits_b200._device import DeviceVector
+    from tests.util import rand_unitary
+    rng = np.random.default_rng(21)
+    d = 8
+    A = qc.Operator.from_matrix(rand_unitary(rng, d))
+    B = qc.Operator.from_matrix(rand_unitary(rng, d))
+    H3 = qc.Operator.from_matrix(rand_unitary(rng, 3))
+    AB = A(B)
+    assert AB._device_only and AB.rank == 2 * d and AB.shape == (2,) * (2 * d)
+    chain = H3(AB, qubit_indices=[5, 0, 2])
+    assert chain._device_only
+    adj = chain.adj
+    assert adj._device_only
+    want_chain = orc.compose_operators(H3._t, orc.compose_operators(A._t, B._t, None), [5, 0, 2])
+    Mc = qc.Operator(np.asarray(want_chain)).to_matrix()
+    # applied to a state without ever materialising the host tensor (dense path, matrix permuted on the device)
+    vec = rand_state_vec(rng, d)
+    got = adj(qc.State.from_column_vector(vec))
+    assert adj._device_only and chain._device_only
+    want = np.conj(Mc.T) @ vec
+    assert rel_err(got.to_column_vector(), want / np.linalg.norm(want)) < 1e-12
+    # on a density operator: U rho U^dagger needs the conjugated matrix, also made on the device
+    rho = qc.State.from_column_vector(vec).density_operator()
+    got_rho = chain(rho)
+    assert chain._device_only
+    out = Mc @ vec
+    assert rel_err(got_rho.to_matrix().reshape(-1), np.outer(out, np.conj(out)).reshape(-1)) < 1e-12
+    # reading the tensor downloads it, and it is the reference's
+    assert rel_err(adj._t.reshape(-1), np.asarray(orc.op_adjoint(np.asarray(want_chain))).reshape(-1)) < 1e-12
+    assert not adj._device_only
+    assert rel_err(adj.to_matrix().reshape(-1), np.conj(Mc.T).reshape(-1)) < 1e-12
+    # adjoint of a host operator of the same size goes through the device too; involution
+    assert rel_err(A.adj.adj._t.reshape(-1), A._t.reshape(-1)) == 0
+    # the kernel itself, both amplitude types, bit 0 moved (pair swap) and bit 0 in place, small and large
+    for dtype in (np.complex64, np.complex128):
+        for n in (6, 16, 20):
+            x = rand_state_vec(rng, n)
+            dv = DeviceVector.from_host(x.reshape([2] * n), dtype)
+            for src_bit in ([b ^ 1 for b in range(n)], [0] + [int(b) for b in 1 + rng.permutation(n - 1)]):
+                got = dv.permuted(src_bit, conj=True).to_host()
+                i = np.arange(2 ** n)
+                j = np.zeros_like(i)
+                for b in range(n):
+                    j |= ((i >> b) & 1) << src_bit[b]
+                ref = np.conj(x.astype(dtype)[j])
+                assert np.array_equal(got, ref.astype(np.complex128)), (dtype, n)
+
+
 @pytest.mark.parametrize('dtype', DTYPES)
 def test_measuring_more_qubits_than_one_chunk(dtype):
     """State.measure of more than MEASURE_CHUNK_BITS qubits (e.g. the default measure() of a large state) draws
