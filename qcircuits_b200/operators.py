@@ -180,26 +180,52 @@ class Operator(OperatorBase):
     def __str__(self):
         return 'Operator for {}-qubit state space. Tensor:\n{}'.format(self.rank // 2, self._t)
 
+    @classmethod
+    def _wrap(cls, array):
+        """An Operator around a fresh complex128 array that nobody else holds (results of the arithmetic below): the
+        private copy of Tensor.__init__ (reference tensors.py:17-18) would be a second 64 MB array for 11 qubits."""
+        if array.dtype != np.complex128:
+            return Operator(array)
+        op = Operator.__new__(Operator)
+        op._t = array
+        return op
+
     def __add__(self, arg):
-        return Operator(self._t + arg._t)
+        return Operator._wrap(self._t + arg._t)
 
     def __sub__(self, arg):
         return self + (-1) * arg
 
     def __neg__(self):
-        return Operator(-self._t)
+        return Operator._wrap(-self._t)
 
     def __mul__(self, scalar):
         if isinstance(scalar, (float, int, complex)):
-            return Operator(scalar * self._t)
+            return Operator._wrap(scalar * self._t)
         return super().__mul__(scalar)
 
     def __rmul__(self, scalar):
         if isinstance(scalar, (float, int, complex)):
-            return Operator(scalar * self._t)
+            return Operator._wrap(scalar * self._t)
 
     def __truediv__(self, scalar):
-        return Operator(self._t / scalar)
+        return Operator._wrap(self._t / scalar)
+
+    def tensor_product(self, arg):
+        """A (x) B (tensors.py:56-76).  From 8 qubits up the product is made on the device (qcs_kron on the flat
+        tensors: the left factor's wires are the high bits) and stays there until its tensor is read."""
+        if (isinstance(arg, Operator) and self.rank + arg.rank >= DEVICE_COMPOSE_MIN_BITS and self.rank > 0 and arg.rank > 0
+                and _cuda_ready()):
+            return Operator._from_device(self._device_tensor().kron(arg._device_tensor()))
+        if isinstance(arg, Operator):
+            return Operator._wrap(np.multiply.outer(self._t, arg._t))
+        return super().tensor_product(arg)
+
+    def tensor_power(self, n):
+        acc = self._t
+        for _ in range(n - 1):
+            acc = np.multiply.outer(acc, self._t)
+        return Operator._wrap(acc) if n > 1 else Operator(acc)
 
     # -- application ---------------------------------------------------------------------------
     def _compose(self, arg, qubit_indices):
@@ -262,39 +288,31 @@ class Operator(OperatorBase):
         key = (np.dtype(dtype).str, conj, _lib.torch().cuda.current_device())
         dev = self._dev_matrix.get(key)
         if dev is None:
-            if self._device_only and np.dtype(dtype) == np.complex128:
-                # device-resident tensor -> matrix (out wires, then in wires) without leaving the device
-                k = self.rank // 2
-                src_bit = [2 * b for b in range(k)] + [2 * b + 1 for b in range(k)]      # flat matrix bit <- tensor bit
-                dev = self._dev_tensor.permuted(src_bit, conj=conj).buf
+            # tensor (interleaved wires) -> matrix (out wires, then in wires) on the device: flat matrix bit b <- tensor
+            # bit 2b (in wire), k + b <- 2b + 1 (out wire); the conjugated copy serves U rho U^dagger
+            from ._device import DeviceVector
+            k = self.rank // 2
+            src_bit = [2 * b for b in range(k)] + [2 * b + 1 for b in range(k)]
+            if np.dtype(dtype) == np.complex128:
+                dvt = self._device_tensor()
             else:
-                M = self._plan().full
-                if M is None:
-                    M = np.ascontiguousarray(self.to_matrix())
-                dev = _lib.upload(np.conj(M) if conj else M, dtype)
+                dvt = DeviceVector.from_host(self._t, dtype)
+            dev = dvt.permuted(src_bit, conj=conj).buf
             self._dev_matrix[key] = dev
         return dev
 
     def _plan(self):
-        """Structure of the matrix, cached: see _gates.analyze.  Operators wider than the tile engine's ops go to the
+        """Structure of the matrix, cached: see _gates.analyze.  Operators wider than ANALYZE_MAX_QUBITS go to the
         dense kernel, which has no use for control / target structure: they skip the analysis (a scan per qubit of
-        a 2^k x 2^k matrix -- it was 2/3 of the run time of examples/grover_algorithm.py at d = 10) and only learn
-        whether they are diagonal, in one pass."""
+        a 2^k x 2^k matrix -- it was 2/3 of the run time of examples/grover_algorithm.py at d = 10) and never build
+        the host matrix at all."""
         if self._plan_cache is None:
             k = self.rank // 2
-            if k > _gates.ANALYZE_MAX_QUBITS and self._device_only:
-                # composed on the device: dense, and its matrix is made there too (_device_matrix)
-                self._plan_cache = _gates.GatePlan(k, [], list(range(k)), False, None, None)
-                return self._plan_cache
-            M = np.ascontiguousarray(self.to_matrix())
             if k > _gates.ANALYZE_MAX_QUBITS:
-                diag = np.diag(M)
-                if np.count_nonzero(M) == np.count_nonzero(diag):
-                    self._plan_cache = _gates.GatePlan(k, [], list(range(k)), True, np.ascontiguousarray(diag), M)
-                else:
-                    self._plan_cache = _gates.GatePlan(k, [], list(range(k)), False, M, M)
+                # dense-kernel operand: its matrix is made on the device from the tensor (_device_matrix)
+                self._plan_cache = _gates.GatePlan(k, [], list(range(k)), False, None, None)
             else:
-                self._plan_cache = _gates.analyze(M)
+                self._plan_cache = _gates.analyze(np.ascontiguousarray(self.to_matrix()))
         return self._plan_cache
 
 
