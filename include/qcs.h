@@ -38,6 +38,8 @@ extern "C" {
 #define QCS_ERR_ARG (-1)
 #define QCS_ERR_CUDA (-2)
 #define QCS_ERR_UNSUPPORTED (-3)
+#define QCS_ERR_NOMEM (-4) /* qcs_dist_alloc: the device allocation failed                       */
+#define QCS_ERR_PEER (-5)  /* multi-GPU: peer access / CUDA IPC between the devices is unavailable */
 
 #define QCS_C64 0  /* complex64  amplitudes (float2)  */
 #define QCS_C128 1 /* complex128 amplitudes (double2) */
@@ -190,6 +192,46 @@ int qcs_outer_accumulate(void *rho, const void *psi, int n, int dtype, double p,
  * (same interleaved row / column layout on 2 * nkeep bits).  out must not alias rho. */
 int qcs_partial_trace(void *out, const void *rho, int d, int dtype, const int32_t *keep, int nkeep,
                       qcs_stream stream);
+
+/* ---- multi-GPU: the qubit exchange of a sharded state over NVLink peer memory (north star (4)) ---------------------------
+ * A state of n_local + log2(P) qubits lives on P = 2, 4, 8 or 16 GPUs, shard r holding the amplitudes whose top log2(P)
+ * flat bits ("rank bits") spell r.  The reference has no counterpart (one NumPy array, state.py:20); the operation is
+ * the np.transpose that would bring a high axis down (state.py:117) when that axis is spread over devices.  The
+ * exchange of g (rank bit, local bit) pairs:
+ *     dst_r[i] = src_r'[i']  with  bit local_bits[j] of i' = rank bit global_bits[j] of r,
+ *                                  rank bit global_bits[j] of r' = bit local_bits[j] of i,  all other bits unchanged
+ * (global_bits index the rank bits 0..log2(P)-1, local_bits the flat bits of a shard; complex64 needs local_bits >= 1).
+ * One kernel per GPU moves its 16-byte vectors straight between its own and the peers' HBM (P2P stores, or loads, over
+ * NVLink) -- no NCCL, no pack / unpack pass.  Out of place: dst shards must not alias src shards.  All gate / measurement entry points above
+ * are per device and are simply called once per shard. */
+typedef struct qcs_dist_ctx *qcs_dist_t;
+
+/* One process driving all GPUs: enables peer access between devs[0..ndev-1] (QCS_ERR_PEER if the topology refuses). */
+int qcs_dist_init(int ndev, const int *devs, qcs_dist_t *handle);
+/* dst_shards[r] / src_shards[r] / streams[r] belong to devs[r].  Ordered after the work already queued on every
+ * stream; on return every stream also waits until all peers have finished reading its source shard. */
+int qcs_dist_swap(qcs_dist_t handle, void *const *dst_shards, const void *const *src_shards, int n_local, int dtype,
+                  const int32_t *global_bits, const int32_t *local_bits, int g, const qcs_stream *streams);
+int qcs_dist_destroy(qcs_dist_t handle);
+
+/* One process per GPU (torchrun / MPI): this rank's half of the same exchange, on pointers valid on THIS device -- the
+ * caller's own buffer at index `rank`, mappings made with qcs_ipc_open for the other ranks.
+ *   push = 1 (preferred: remote stores, 682 GB/s per GPU and direction between two B200s): `local` = this rank's SOURCE
+ *            shard, peers[r] = rank r's DESTINATION shard;
+ *   push = 0 (remote loads, 627 GB/s): `local` = this rank's DESTINATION shard, peers[r] = rank r's SOURCE shard.
+ * The caller orders the ranks: every source complete and every destination free before the call, nothing reused before
+ * every rank's call has finished (qcircuits_b200/dist.py brackets it with two one-element NCCL all-reduces on the same
+ * stream).  qcs_dist_swap (one process) pushes unless QCS_DIST_PUSH=0. */
+int qcs_dist_swap_rank(void *local, const void *const *peers, int nranks, int rank, int n_local, int dtype,
+                       const int32_t *global_bits, const int32_t *local_bits, int g, int push, qcs_stream stream);
+/* CUDA IPC plumbing for that mode.  Shards that other processes map must be plain cudaMalloc allocations (a caching
+ * allocator hands out interior pointers): qcs_dist_alloc / qcs_dist_free are the one place libqcs allocates amplitude
+ * memory.  handle64 = the 64 bytes of a cudaIpcMemHandle_t, to be sent to the other ranks by any means. */
+int qcs_dist_alloc(void **ptr, int64_t bytes);
+int qcs_dist_free(void *ptr);
+int qcs_ipc_get_handle(const void *dev_ptr, void *handle64);
+int qcs_ipc_open(const void *handle64, void **mapped);
+int qcs_ipc_close(void *mapped);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,15 @@ PROTOTYPES = {
                              c_void_p, c_void_p, c_void_p]),
     'qcs_diag_probs': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'qcs_partial_trace': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'qcs_dist_init': (c_int, [c_int, c_void_p, c_void_p]),
+    'qcs_dist_swap': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'qcs_dist_destroy': (c_int, [c_void_p]),
+    'qcs_dist_swap_rank': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'qcs_dist_alloc': (c_int, [c_void_p, ctypes.c_int64]),
+    'qcs_dist_free': (c_int, [c_void_p]),
+    'qcs_ipc_get_handle': (c_int, [c_void_p, c_void_p]),
+    'qcs_ipc_open': (c_int, [c_void_p, c_void_p]),
+    'qcs_ipc_close': (c_int, [c_void_p]),
     'qcs_outer_accumulate': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_int, c_void_p]),
 }
 

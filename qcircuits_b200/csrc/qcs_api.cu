@@ -244,4 +244,32 @@ int qcs_outer_accumulate(void *rho, const void *psi, int n, int dtype, double p,
     return misc_outer(rho, psi, n, dtype, p, norm_psi, accumulate, (cudaStream_t)stream);
 }
 
+// ---- multi-GPU exchange (qcs_dist.cu) ------------------------------------------------------------------------------
+int qcs_dist_init(int ndev, const int *devs, qcs_dist_t *handle) {
+    return dist_init(ndev, devs, reinterpret_cast<DistCtx **>(handle));
+}
+int qcs_dist_swap(qcs_dist_t handle, void *const *dst_shards, const void *const *src_shards, int n_local, int dtype,
+                  const int32_t *global_bits, const int32_t *local_bits, int g, const qcs_stream *streams) {
+    if (!global_bits || !local_bits) return set_error(QCS_ERR_ARG, "null bit list");
+    return dist_swap(reinterpret_cast<DistCtx *>(handle), dst_shards, src_shards, n_local, dtype, global_bits, local_bits, g,
+                     reinterpret_cast<const cudaStream_t *>(streams));
+}
+int qcs_dist_destroy(qcs_dist_t handle) { return dist_destroy(reinterpret_cast<DistCtx *>(handle)); }
+int qcs_dist_swap_rank(void *local, const void *const *peers, int nranks, int rank, int n_local, int dtype,
+                       const int32_t *global_bits, const int32_t *local_bits, int g, int push, qcs_stream stream) {
+    if (!local || !peers || !global_bits || !local_bits) return set_error(QCS_ERR_ARG, "null argument");
+    return dist_swap_rank(local, peers, nranks, rank, n_local, dtype, global_bits, local_bits, g, push, (cudaStream_t)stream);
+}
+int qcs_dist_alloc(void **ptr, int64_t bytes) { return dist_alloc(ptr, bytes); }
+int qcs_dist_free(void *ptr) { return dist_free(ptr); }
+int qcs_ipc_get_handle(const void *dev_ptr, void *handle64) {
+    if (!dev_ptr || !handle64) return set_error(QCS_ERR_ARG, "null argument");
+    return ipc_get_handle(dev_ptr, handle64);
+}
+int qcs_ipc_open(const void *handle64, void **mapped) {
+    if (!handle64 || !mapped) return set_error(QCS_ERR_ARG, "null argument");
+    return ipc_open(handle64, mapped);
+}
+int qcs_ipc_close(void *mapped) { return ipc_close(mapped); }
+
 }  // extern "C"

@@ -146,4 +146,18 @@ int misc_apply_uf(void *dst, const void *src, int n, int dtype, const uint32_t *
 int misc_dense(void *dst, const void *src, int n, int dtype, const void *dev_matrix, int k, const int32_t *bitpos,
                const double *norm_in, double *norm_out, void *ws, cudaStream_t st);
 
+struct DistCtx;
+int dist_init(int ndev, const int *devs, DistCtx **out);
+int dist_destroy(DistCtx *h);
+int dist_swap(DistCtx *h, void *const *dst_shards, const void *const *src_shards, int n_local, int dtype,
+              const int32_t *global_bits, const int32_t *local_bits, int g, const cudaStream_t *streams);
+int dist_swap_rank(void *dst, const void *const *peer_src, int nranks, int rank, int n_local, int dtype,
+                   const int32_t *global_bits, const int32_t *local_bits, int g, int push, cudaStream_t st);
+bool dist_push_mode();
+int ipc_get_handle(const void *dev_ptr, void *handle64);
+int ipc_open(const void *handle64, void **mapped);
+int ipc_close(void *mapped);
+int dist_alloc(void **ptr, int64_t bytes);
+int dist_free(void *ptr);
+
 }  // namespace qcs

@@ -16,6 +16,9 @@ top g physical bits equal r.  Which *logical* qubit sits on which *physical* bit
 ``dist_schedule`` is pure host logic and is the same on every rank; it is exercised on CPU (gloo,
 world_size 2) in tests/test_dist_cpu.py with a NumPy engine standing in for the kernels.
 """
+import ctypes
+import os
+
 import numpy as np
 
 from . import _lib
@@ -182,15 +185,58 @@ class _LogicalGate:
 # ---------------------------------------------------------------------------------------------------
 # engines: what a rank does to its shard (CUDA in the product; tests plug in a NumPy checker)
 # ---------------------------------------------------------------------------------------------------
+class _PeerShard:
+    """A shard allocated with qcs_dist_alloc (a plain cudaMalloc block, so that its CUDA IPC handle names exactly this
+    buffer) and exposed to torch through __cuda_array_interface__; freed when the last tensor over it goes away."""
+
+    def __init__(self, nreals, real_typestr, itemsize):
+        ptr = ctypes.c_void_p()
+        _lib.check(_lib.load().qcs_dist_alloc(ctypes.byref(ptr), nreals * itemsize))
+        self.ptr = ptr.value
+        self.__cuda_array_interface__ = {'shape': (nreals,), 'typestr': real_typestr, 'data': (self.ptr, False), 'version': 2}
+
+    def __del__(self):
+        try:
+            _lib.load().qcs_dist_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def _exchange_mode():
+    """'p2p' (default): the exchange is libqcs's own kernel pulling from the peers' HBM over NVLink (qcs_dist_swap_rank);
+    'nccl': torch.distributed.all_to_all_single."""
+    return os.environ.get('QCS_DIST_EXCHANGE', 'p2p')
+
+
 class CudaEngine:
     """Shard + spare buffer on the current CUDA device; passes run through libqcs."""
 
+    P2P_MIN_LOCAL_BITS = 13
+
     def __init__(self, n_local, dtype):
         self.n_local, self.dtype = n_local, np.dtype(dtype)
-        self.buf = _lib.alloc_amplitudes(n_local, dtype)
-        self.spare = _lib.alloc_amplitudes(n_local, dtype)
         self.code = _lib.dtype_code(dtype)
+        self._p2p = _exchange_mode() == 'p2p'
+        self._peer_map = {}        # local data_ptr -> [pointer to that buffer's counterpart on every rank]
+        self._opened = []          # mappings to close before the next registration
+        self._retired = []         # old shards that peers may still have mapped
+        self.buf = self._alloc_shard(n_local)
+        self.spare = self._alloc_shard(n_local)
         self.launches = 0
+        self.exchange_kind = None
+
+    def _alloc_shard(self, n_local):
+        if not self._p2p:
+            return _lib.alloc_amplitudes(n_local, self.dtype)
+        t = _lib.require_cuda()
+        c64 = self.dtype == np.dtype(np.complex64)
+        holder = _PeerShard(2 << n_local, '<f4' if c64 else '<f8', 4 if c64 else 8)
+        return t.as_tensor(holder, device='cuda')
+
+    def _retire(self, tensor):
+        """keep a replaced shard alive until the peers have dropped their mappings (next registration)"""
+        if self._p2p and tensor.data_ptr() in self._peer_map:
+            self._retired.append(tensor)
 
     def set_basis(self, index):
         lib = _lib.load()
@@ -223,9 +269,81 @@ class CudaEngine:
         self.launches += 1
 
     def exchange(self, group=None):
+        """all rank bits <-> the top g local bits: block p of rank r goes to block r of rank p"""
         import torch.distributed as dist
-        dist.all_to_all_single(self.spare, self.buf, group=group)
+        world = dist.get_world_size(group)
+        if self._p2p and self.n_local >= self.P2P_MIN_LOCAL_BITS and world <= 16 and self._register_peers(group):
+            self._exchange_p2p(group, world)
+            self.exchange_kind = 'p2p'
+        else:
+            dist.all_to_all_single(self.spare, self.buf, group=group)
+            self.exchange_kind = 'nccl'
         self.buf, self.spare = self.spare, self.buf
+
+    def _register_peers(self, group):
+        """Map the peers' shard and spare buffers into this process (CUDA IPC), once per pair of buffers.  Collective;
+        returns False on every rank if any rank cannot map (the exchange then falls back to NCCL for good)."""
+        import torch.distributed as dist
+        if self.buf.data_ptr() in self._peer_map and self.spare.data_ptr() in self._peer_map:
+            return True
+        t = _lib.require_cuda()
+        lib = _lib.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        for m in self._opened:
+            lib.qcs_ipc_close(ctypes.c_void_p(m))
+        self._opened, self._peer_map = [], {}
+        handles = (ctypes.c_ubyte * 128)()
+        ok = 1
+        for k, tensor in enumerate((self.buf, self.spare)):
+            if lib.qcs_ipc_get_handle(ctypes.c_void_p(tensor.data_ptr()), ctypes.byref(handles, 64 * k)) != 0:
+                ok = 0
+        mine = t.tensor(list(handles) + [ok], dtype=t.uint8, device='cuda')
+        everyone = t.empty(world * 129, dtype=t.uint8, device='cuda')
+        dist.all_gather_into_tensor(everyone, mine, group=group)      # (also: every rank has closed its old mappings)
+        self._retired = []
+        table = everyone.cpu().numpy().reshape(world, 129)
+        ok = int(table[:, 128].min())
+        maps = {self.buf.data_ptr(): [0] * world, self.spare.data_ptr(): [0] * world}
+        if ok:
+            for k, tensor in enumerate((self.buf, self.spare)):
+                for r in range(world):
+                    if r == rank:
+                        maps[tensor.data_ptr()][r] = tensor.data_ptr()
+                        continue
+                    raw = (ctypes.c_ubyte * 64)(*[int(x) for x in table[r, 64 * k:64 * k + 64]])
+                    mapped = ctypes.c_void_p()
+                    if lib.qcs_ipc_open(raw, ctypes.byref(mapped)) != 0:
+                        ok = 0
+                        break
+                    self._opened.append(mapped.value)
+                    maps[tensor.data_ptr()][r] = mapped.value
+        flag = t.tensor([ok], dtype=t.int32, device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            for m in self._opened:
+                lib.qcs_ipc_close(ctypes.c_void_p(m))
+            self._opened, self._p2p = [], False
+            return False
+        self._peer_map = maps
+        return True
+
+    def _exchange_p2p(self, group, world):
+        import torch.distributed as dist
+        t = _lib.require_cuda()
+        g = int(round(np.log2(world)))
+        rank = dist.get_rank(group)
+        if not hasattr(self, '_flag'):
+            self._flag = t.zeros(1, dtype=t.int32, device='cuda')
+        push = int(os.environ.get('QCS_DIST_PUSH', '1')) != 0      # remote stores (682 GB/s) beat remote loads (627 GB/s)
+        local, table = (self.buf, self.spare) if push else (self.spare, self.buf)
+        peers = (ctypes.c_void_p * world)(*self._peer_map[table.data_ptr()])
+        dist.all_reduce(self._flag, group=group)       # device-side barrier: every rank's shard is complete, its spare free
+        _lib.check(_lib.load().qcs_dist_swap_rank(local.data_ptr(), peers, world, rank, self.n_local, self.code,
+                                                  _lib.int32_array(list(range(g))),
+                                                  _lib.int32_array([self.n_local - g + j for j in range(g)]), g,
+                                                  1 if push else 0, _lib.stream_ptr()))
+        dist.all_reduce(self._flag, group=group)       # ... and nobody rewrites a shard its peers are still reading
+        self.launches += 1
 
     def norm2(self):
         out = _lib.alloc_scalar()
@@ -253,13 +371,15 @@ class CudaEngine:
         lib = _lib.load()
         m = len(bitpos)
         n_out = self.n_local - m if remove else self.n_local
-        dst = _lib.alloc_amplitudes(n_out, self.dtype) if remove else self.spare
+        dst = self._alloc_shard(n_out) if remove else self.spare
         _lib.check(lib.qcs_collapse(dst.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, _lib.int32_array(bitpos), m,
                                     int(outcome), 1 if remove else 0, float(scale), None, _lib.workspace().data_ptr(),
                                     _lib.stream_ptr()))
         if remove:
+            self._retire(self.buf)
+            self._retire(self.spare)
             self.buf, self.n_local = dst, n_out
-            self.spare = _lib.alloc_amplitudes(n_out, self.dtype)
+            self.spare = self._alloc_shard(n_out)
         else:
             self.buf, self.spare = self.spare, self.buf
         self.launches += 1
@@ -269,18 +389,18 @@ class CudaEngine:
         vec = np.asarray(vec).reshape(-1)
         nb = int(round(np.log2(vec.size)))
         small = _lib.upload(vec, self.dtype)
-        dst = _lib.alloc_amplitudes(self.n_local + nb, self.dtype)
+        dst = self._alloc_shard(self.n_local + nb)
         _lib.check(_lib.load().qcs_kron(dst.data_ptr(), self.buf.data_ptr(), self.n_local, small.data_ptr(), nb, self.code,
                                         None, None, None, None, _lib.stream_ptr()))
+        self._retire(self.buf)
+        self._retire(self.spare)
         self.n_local += nb
         self.buf = dst
-        self.spare = _lib.alloc_amplitudes(self.n_local, self.dtype)
+        self.spare = self._alloc_shard(self.n_local)
 
     def clone(self):
-        other = CudaEngine.__new__(CudaEngine)
-        other.n_local, other.dtype, other.code, other.launches = self.n_local, self.dtype, self.code, 0
-        other.buf = self.buf.clone()
-        other.spare = _lib.alloc_amplitudes(self.n_local, self.dtype)
+        other = CudaEngine(self.n_local, self.dtype)
+        other.buf.copy_(self.buf)
         return other
 
     def marginals(self, bitpos):

@@ -8,7 +8,7 @@ out=$root/build/$name
 mkdir -p $out/obj
 cd $root/qcircuits_b200/csrc
 [ -f qcs_regops.inc ] || python3 gen_regops.py > qcs_regops.inc
-for f in qcs_api qcs_tile qcs_misc; do
+for f in qcs_api qcs_tile qcs_misc qcs_dist; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -c $f.cu -o $out/obj/$f.o &
 done
 wait
