@@ -187,7 +187,11 @@ def main(args, parity_check=None):
                          'combined': {'hbm_plus_nvlink_roofline_ms': t_roof, 'measured_ms': ms_per_step,
                                       'frac': t_roof / ms_per_step, 'nvlink_gbs_per_dir': nvlink,
                                       'exchange_ms_measured': exchange_ms,
-                                      'exchange_gbs_per_gpu': sent / (exchange_ms * 1e-3) / 1e9}},
+                                      'exchange_gbs_per_gpu': sent / (exchange_ms * 1e-3) / 1e9,
+                                      'exchange_kernel': {'p2p': 'qcs::dist_pull_kernel (libqcs: P2P stores into the peers\' shards over '
+                                                                 'NVLink, CUDA IPC; two one-element NCCL all-reduces order the ranks)',
+                                                          'nccl': 'torch.distributed.all_to_all_single (NCCL)'}.get(
+                                          getattr(st.engine, 'exchange_kind', None), 'unknown')}},
             'cpu_baseline': None,
             # per-GPU work rate, comparable across N and with the single-GPU line: gates x 2^n amplitudes / time / GPUs
             'amp_updates_per_s_per_gpu': ngates * 2.0 ** n / (ms_per_step * 1e-3) / world,
