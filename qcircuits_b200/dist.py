@@ -327,6 +327,18 @@ class CudaEngine:
         self._peer_map = maps
         return True
 
+    def release_peers(self, group=None):
+        """Collective: drop every mapping of the peers' shards (CUDA IPC) so that the owners can really free them.  Call
+        it before discarding a large sharded state inside a long-lived process group; the next exchange maps again."""
+        import torch.distributed as dist
+        lib = _lib.load()
+        _lib.require_cuda().cuda.current_stream().synchronize()
+        for m in self._opened:
+            lib.qcs_ipc_close(ctypes.c_void_p(m))
+        self._opened, self._peer_map = [], {}
+        dist.barrier(group)
+        self._retired = []
+
     def _exchange_p2p(self, group, world):
         import torch.distributed as dist
         t = _lib.require_cuda()

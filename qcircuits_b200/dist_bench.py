@@ -74,6 +74,7 @@ def main(args, parity_check=None):
     xms = torch.tensor([x0.elapsed_time(x1) / 2], dtype=torch.float64, device='cuda')
     dist.all_reduce(xms, op=dist.ReduceOp.MAX)
     exchange_ms = float(xms.item())
+    exchange_kind = getattr(st.engine, 'exchange_kind', None)
 
     # end to end: every rank's shard comes from host memory and the result goes back to host memory inside the timed
     # region, through a BOUNDED pinned staging ring (4 x 256 MiB per rank) -- whole pinned shards (2 x 64 GiB per rank)
@@ -138,6 +139,8 @@ def main(args, parity_check=None):
     # single-GPU leg), device-resident like `value`
     strong = None
     if not args.skip_strong:
+        if hasattr(st.engine, 'release_peers'):
+            st.engine.release_peers()          # peers unmap this rank's shards before they are freed
         st.engine.buf = st.engine.spare = None          # 2 x 64 GiB back before the next state is allocated
         del st
         torch.cuda.empty_cache()
@@ -161,6 +164,8 @@ def main(args, parity_check=None):
         strong = {'qubits': ns, 'gates': len(circ_s), 'ms_per_step': float(sms.item()),
                   'gates_per_s': len(circ_s) / (float(sms.item()) * 1e-3), 'norm_check': st_s.norm2(),
                   'amp_updates_per_s_per_gpu': len(circ_s) * 2.0 ** ns / (float(sms.item()) * 1e-3) / world}
+        if hasattr(st_s.engine, 'release_peers'):
+            st_s.engine.release_peers()
         del st_s
 
 
@@ -182,7 +187,7 @@ def main(args, parity_check=None):
                        'exchanges_per_step': exchanges, 'max_ops_per_pass': args.max_ops,
                        'l2': 'shard (%.0f GiB) is far larger than L2; no flush needed' % (shard_bytes / 2 ** 30)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'kernel': 'qcs::tile_kernel_pipe (fused gate pass), per GPU',
+                         'traffic': None, 'peak_source': peak_src, 'kernel': 'qcs::tile_kernel_tc / tile_kernel_pipe (fused gate passes), per GPU',
                          'bytes_per_launch': pass_bytes,
                          'combined': {'hbm_plus_nvlink_roofline_ms': t_roof, 'measured_ms': ms_per_step,
                                       'frac': t_roof / ms_per_step, 'nvlink_gbs_per_dir': nvlink,
@@ -191,7 +196,7 @@ def main(args, parity_check=None):
                                       'exchange_kernel': {'p2p': 'qcs::dist_pull_kernel (libqcs: P2P stores into the peers\' shards over '
                                                                  'NVLink, CUDA IPC; two one-element NCCL all-reduces order the ranks)',
                                                           'nccl': 'torch.distributed.all_to_all_single (NCCL)'}.get(
-                                          getattr(st.engine, 'exchange_kind', None), 'unknown')}},
+                                          exchange_kind, 'unknown')}},
             'cpu_baseline': None,
             # per-GPU work rate, comparable across N and with the single-GPU line: gates x 2^n amplitudes / time / GPUs
             'amp_updates_per_s_per_gpu': ngates * 2.0 ** n / (ms_per_step * 1e-3) / world,
