@@ -96,6 +96,16 @@ int qcs_apply_dense(void *dst, const void *src, int n, int dtype, const void *de
 int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
                     const double *norm_in, double *norm_out, void *ws, qcs_stream stream);
 
+/* The same pass for a caller that does not keep the lazy norm but knows a bound (the sharded engine: the norm
+ * belongs to the whole state, not to a shard).  bound2_in: device scalar >= the squared 2-norm of src, or NULL.
+ * It only RANGES the fp16 operands of the tensor-core sweeps (complex64; amplitudes are scaled by a power of two so
+ * that the bound maps to 2^15; the error of a sweep is about 2^-40 of the bound, so a bound within a few powers of
+ * two of the largest amplitude times 2^(n/2) keeps the 1e-5 tolerance); the result is not scaled by it.  With
+ * norm_in == NULL and bound2_in == NULL the library measures the norm itself (one extra read of src). */
+int qcs_apply_fused_bounded(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
+                            const double *norm_in, double *norm_out, const double *bound2_in, void *ws,
+                            qcs_stream stream);
+
 /* Planning only, no launch and no device needed (diagnostics for the fusion scheduler and the tests):
  * how the tile engine would run this pass.  stats[0..5] = tile bits, sweeps, register ops, shared-memory
  * dense ops, tile-level predicates, scale mode; stats[6] = number of input ops that run in the last sweep and
@@ -110,10 +120,11 @@ int qcs_plan_order(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats
 
 /* Planning only, complex64: the tensor-core sweeps of the pass (north_star (1): "fused blocks ... run on tensor
  * cores").  A sweep multiplies a run of gates into one dense 2^5 x 2^5 block on five tile bits (the contraction
- * of operators.py:261 for all of them at once) and applies it with tcgen05.mma kind::tf32 as a 3-term split.
+ * of operators.py:261 for all of them at once) and applies it with tcgen05.mma kind::f16 as a two-term split of
+ * both operands (hi.hi + hi.lo + lo.hi, fp32 accumulation); passes with a non-unitary op are not taken.
  * stats as qcs_plan_stats, with stats[7] = sweeps with a block | (input ops inside blocks) << 8.
- * images: 4 slots x 16384 bytes, the shared-memory operand images ("hi" tf32 image then "lo" image; K-major, no
- * swizzle: row r, column c at byte (r%8)*16 + (r/8)*1024 + (c/4)*128 + (c%4)*4; rows 0..31 = Re U, 32..63 = Im U).
+ * images: 8 slots x 8192 bytes, the shared-memory operand images ("hi" fp16 image then "lo" image; K-major, no
+ * swizzle: row r, column c at byte (r%8)*16 + (r/8)*512 + (c/8)*128 + (c%8)*2; rows 0..31 = Re U, 32..63 = Im U).
  * info: 8 int32 per block: flat bits of block-index bits 0..4, register ops before the block, slot, sweep index.
  * Returns QCS_ERR_UNSUPPORTED when the pass has no dense block (it then runs on the register-sweep kernel). */
 int qcs_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *images, int32_t *info);

@@ -46,6 +46,8 @@ PROTOTYPES = {
     'qcs_plan_stats': (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     'qcs_apply_fused': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    'qcs_apply_fused_bounded': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     'qcs_abs2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'qcs_dot': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'qcs_scale': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,

@@ -109,15 +109,20 @@ int qcs_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *im
     return tile_plan_blocks(n, ops, nops, stats, images, info);
 }
 
-int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
-                    double *norm_out, void *ws, qcs_stream stream) {
+int qcs_apply_fused_bounded(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
+                            double *norm_out, const double *bound2_in, void *ws, qcs_stream stream) {
     if (int e = check_state(dst, n, dtype)) return e;
     if (int e = check_state(src, n, dtype)) return e;
     if (!ops || nops < 1 || nops > QCS_MAX_OPS) return set_error(QCS_ERR_ARG, "op count must be in 1..QCS_MAX_OPS");
     if (norm_out && !ws) return set_error(QCS_ERR_ARG, "norm_out needs a workspace");
     for (int i = 0; i < nops; ++i)
         if (!ops[i].matrix) return set_error(QCS_ERR_ARG, "op without a matrix");
-    return tile_apply(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, (cudaStream_t)stream);
+    return tile_apply(dst, src, n, dtype, ops, nops, norm_in, norm_out, bound2_in, ws, (cudaStream_t)stream);
+}
+
+int qcs_apply_fused(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
+                    double *norm_out, void *ws, qcs_stream stream) {
+    return qcs_apply_fused_bounded(dst, src, n, dtype, ops, nops, norm_in, norm_out, nullptr, ws, stream);
 }
 
 int qcs_apply_gate(void *dst, const void *src, int n, int dtype, const double *matrix, int k, const int32_t *bitpos,

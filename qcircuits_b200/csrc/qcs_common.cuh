@@ -40,9 +40,10 @@ __device__ __forceinline__ uint32_t insert_zero32(uint32_t x, int p) {
 // ws + PROGRAM_OFFSET  : (unused, reserved)
 constexpr int WS_PARTIALS_OFFSET = 256;
 constexpr int MAX_GRID = 148 * 8;
-// ws + 32768          : tensor-core block-matrix images of the pass in flight, 4 slots x 16 KB (qcs_internal.h)
+// ws + 32640          : squared norm of the source of a tensor-core pass whose caller gave none
+// ws + 32768          : tensor-core block-matrix images of the pass in flight, 8 slots x 8 KB (qcs_internal.h)
 constexpr int64_t WS_BYTES = 32768 + 4 * 16384;
-static_assert(WS_PARTIALS_OFFSET + 2 * MAX_GRID * 8 + 1024 <= 32768, "reduction scratch overlaps the matrix images");
+static_assert(WS_PARTIALS_OFFSET + 2 * MAX_GRID * 8 + 1024 <= 32640, "reduction scratch overlaps the matrix images");
 
 // Deterministic grid-wide sum of NV doubles per thread: per-CTA partials are written to the
 // workspace, the CTA that takes the last ticket adds them in a fixed order and stores the result.

@@ -49,7 +49,7 @@ struct RegOp {                   // 16 bytes, read with one 128-bit shared-memor
 };
 struct OuterPred { uint64_t care, val; };   // flat-index bits outside the tile
 constexpr int SWEEP_REG = 0, SWEEP_GENERIC = 1;
-struct alignas(8) Sweep {
+struct alignas(16) Sweep {
     int32_t kind, first, count, nreg;
     int8_t rpos[REG_BITS_MAX];       // tile-local positions of the register bits, ascending
     int16_t thread_phase;            // some PHASE op of the sweep is uniform over a thread's amplitudes
@@ -63,10 +63,11 @@ struct alignas(8) Sweep {
     // thread and sweep instead of ~19 dependent ones): rpos[j] at bits 4j (j < 4), hrank at 16, tc_slot + 1 at 20,
     // flags at 24 (1: has register ops, 2: dense2 interpreter, 4: thread phase), first register op at 32
     uint64_t packed;                 // (8-byte aligned: read with one 64-bit shared-memory load)
+    uint64_t pad_;
     // host-precomputed addressing of the compile-time-geometry path: inserting a zero at rpos[j] is
     // x += x & himask[j]; stride[j] = padded shared-memory distance in bytes between the two values of bit j
+    uint32_t stride[REG_BITS_MAX];   // (16-byte aligned: the tensor-core kernel reads the four with one 128-bit load)
     uint32_t himask[REG_BITS_MAX];
-    uint32_t stride[REG_BITS_MAX];
 };
 
 template <int NSW, int NREG, int NGEN, int MATBYTES>
@@ -82,6 +83,7 @@ struct TileProgram {
     double *norm_out;
     void *ws;
     const void *tc_mats;             // device: n_tc block-matrix images of TC_SLOT_BYTES each (tile_kernel_tc)
+    const double *tc_norm;           // device: squared norm of src (or an upper bound): ranges the fp16 tensor-core operands
     int32_t n_tc, tc_pad;
     Sweep sweeps[NSW];
     RegOp regops[NREG];
@@ -96,16 +98,20 @@ using TcProg = TileProgram<24, 192, 8, 6144>;
 
 // ---- tensor-core sweeps (complex64, 12-bit tiles) ------------------------------------------------
 // A sweep's dense block acts on 5 tile bits: a (2^5 x 2^5 complex) matrix applied to the 128 rows x 32 amplitudes
-// of a tile, as 3 x 12 tcgen05.mma kind::tf32 instructions (3-term split: lo*hi + hi*lo + hi*hi).
+// of a tile, as 3 x 6 tcgen05.mma kind::f16 instructions (fp16 operands, fp32 accumulation; two-term split of both
+// operands: hi*hi + hi*lo + lo*hi, the amplitudes ranged by a power of two taken from the norm of the state).
 constexpr int TC_BLOCK_BITS = 5;
-constexpr int TC_MAX_SLOTS = 4;                      // block matrices resident in shared memory per pass
-constexpr int TC_HALF_BYTES = 64 * 32 * 4;           // one image: rows 0..31 = Re U, rows 32..63 = Im U; K-major, no swizzle
-constexpr int TC_SLOT_BYTES = 2 * TC_HALF_BYTES;     // tf32 "hi" image, then the "lo" image
+constexpr int TC_MAX_SLOTS = 8;                      // block matrices resident in shared memory per pass
+constexpr int TC_HALF_BYTES = 64 * 32 * 2;           // one fp16 image: rows 0..31 = Re U, rows 32..63 = Im U; K-major, no swizzle
+constexpr int TC_SLOT_BYTES = 2 * TC_HALF_BYTES;     // "hi" image = fp16(U), then the "lo" image = fp16(U - hi)
+constexpr int TC_DEFAULT_SLOTS = 6;                  // what the planner uses unless QCS_TC_SLOTS says otherwise
+constexpr int64_t WS_TC_NORM_OFFSET = 32640;         // squared norm of src when the caller gave none (tile_apply computes it)
 constexpr int TC_GROUP_THREADS = 256;                // two groups per CTA, each streams its own tiles
 constexpr int TC_STAGES = 2;                         // ring stages per group
 constexpr int64_t WS_TC_OFFSET = 32768;              // block-matrix images live in the caller's workspace from here
 constexpr int TC_UPLOAD_RING = 8;                    // pinned host staging sets for their upload (one per launch in flight)
-static_assert(sizeof(Sweep) % 8 == 0 && offsetof(Sweep, packed) % 8 == 0, "Sweep::packed is read with one 64-bit load");
+static_assert(sizeof(Sweep) % 16 == 0 && offsetof(Sweep, packed) % 8 == 0 && offsetof(Sweep, stride) % 16 == 0,
+              "Sweep::packed is read with one 64-bit load, Sweep::stride with one 128-bit load");
 static_assert(sizeof(LargeProg) < 32000, "kernel parameter space is 32764 bytes");
 
 struct DeviceInfo { int sms; size_t smem_per_sm; };
@@ -116,7 +122,7 @@ int tune_int(const char *name, int fallback);
 int set_error(int code, const char *msg);
 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
-               double *norm_out, void *ws, cudaStream_t stream);
+               double *norm_out, const double *bound_in, void *ws, cudaStream_t stream);
 
 int tile_plan_stats(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats);
 int tile_plan_order(int n, int dtype, const qcs_op *ops, int nops, int32_t *stats, int32_t *sweep_of_op);

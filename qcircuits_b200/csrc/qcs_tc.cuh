@@ -1,26 +1,40 @@
-// Tensor-core sweeps of the tile engine (complex64, 12-bit tiles): tcgen05.mma kind::tf32, accumulators in
+// Tensor-core sweeps of the tile engine (complex64, 12-bit tiles): tcgen05.mma kind::f16, accumulators in
 // tensor memory.  Included by qcs_tile.cu after the register-sweep machinery.
 //
 // The contraction replaced is the same np.tensordot as everywhere (reference operators.py:261), for a run of
 // gates that the planner has multiplied into ONE dense 2^5 x 2^5 complex block U acting on five tile bits.
 //
 // Mapping.  A tile holds 2^12 amplitudes = 128 rows x 32 amplitudes, the 32 spanned by the block's five bits.
-//   A (M = 128 rows, K): the tile, in TENSOR MEMORY -- lane = row, columns = [Re a_0..a_31 | Im a_0..a_31], written
-//       by the thread that owns the row with tcgen05.st straight from the registers of the sweep (no second
-//       shared-memory image of the tile).  Two copies: tf32 "hi" = round(a), "lo" = a - hi (exact).
-//   B (N, K): the block matrix in SHARED MEMORY, K-major, no swizzle, rows 0..31 = Re U, rows 32..63 = Im U; a "hi"
-//       and a "lo" image, built on the host from the float64 product of the gates.
-//   D (M = 128, N = 64) in tensor memory: columns [Re out_0..31 | Im out_0..31], read back with tcgen05.ld by the same
-//       thread into the same registers, which then go back to the tile in shared memory.
+//   A (M = 128 rows, K): the tile, in TENSOR MEMORY, fp16 packed two per 32-bit column -- lane = row; thread (row, h)
+//       writes its 16 amplitudes as 8 columns of real parts, then 8 of imaginary parts, with ONE tcgen05.st.x16 per
+//       image straight from the registers of the sweep (no second shared-memory image of the tile).
+//       Two images: "hi" = fp16(s a), "lo" = fp16(s a - hi); s = a power of two that maps the norm of the state to
+//       [2^14, 2^15) -- every amplitude is at most the norm, so nothing overflows, and an amplitude below the fp16
+//       normal range still carries an absolute error of only 2^-25 / s ~ 2^-40 of the norm (subnormals are exact to 2^-24).
+//   B (N, K): the block matrix in SHARED MEMORY, fp16, K-major, no swizzle, rows 0..31 = Re U, rows 32..63 = Im U; a
+//       "hi" and a "lo" image, built on the host from the float64 product of the gates (8 KB per block).
+//   D (M = 128, N = 64, fp32) in tensor memory: columns [Re out_0..31 | Im out_0..31], read back with tcgen05.ld by the
+//       same thread into the same registers (times 1 / s), which then go back to the tile in shared memory.
 //   Re out = Re a . Re U^T - Im a . Im U^T ,  Im out = Re a . Im U^T + Im a . Re U^T :
-//       per split term 4 instructions M128 N64 K8 (Re a against both halves of B) + 4 M128 N32 K8 with the b-negate
-//       flag (Im a against Im U, into the Re columns) + 4 M128 N32 K8 (Im a against Re U, into the Im columns);
-//       three terms, small ones first: lo.hi + hi.lo + hi.hi.  36 instructions, ~780 cycles per tile and sweep
-//       (measured floors: 32.3 / 16.3 cycles per instruction, tools/probe/tc_probe.cu).
+//       per split term 2 instructions M128 N64 K16 (Re a against both halves of B) + 2 M128 N32 K16 with the b-negate
+//       flag (Im a against Im U, into the Re columns) + 2 M128 N32 K16 (Im a against Re U, into the Im columns);
+//       three terms, small ones first: lo.hi + hi.lo + hi.hi (the dropped lo.lo is 2^-24).  18 instructions per tile
+//       and sweep, half the tensor-pipe time and half the shared-memory operand reads of the tf32 form it replaced.
 // One elected lane issues the instructions after the group's barrier; completion comes back through
 // tcgen05.commit on an mbarrier.  A CTA is two groups of 256 threads that stream different tiles, so one group's
 // shared-memory and split work overlaps the other group's MMAs.
 #pragma once
+#include <cuda_fp16.h>
+
+#ifdef QCS_TC_DBG
+// timing experiments only: clock stamps of group 0, CTA 0 (thread 0) for a few steady-state tiles
+__device__ unsigned long long g_tc_trace[4096];
+__device__ unsigned int g_tc_trace_n;
+#define TC_STAMP(ctx, tag) do { if ((ctx).trace_on && (ctx).trace_i < 2040u) { \
+    g_tc_trace[2 * (ctx).trace_i] = (unsigned long long)(tag); g_tc_trace[2 * (ctx).trace_i + 1] = clock64(); ++(ctx).trace_i; } } while (0)
+#else
+#define TC_STAMP(ctx, tag) do { } while (0)
+#endif
 
 namespace tc {
 
@@ -61,7 +75,7 @@ __device__ __forceinline__ void commit(uint64_t *bar) {
 // D[tmem] (+)= A[tmem] . B[smem]^T
 __device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
@@ -70,10 +84,10 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor, kind::tf32: D = f32 (bit 4), A and B = tf32 (2 at bits 7 and 10), b-negate bit 14,
+// instruction descriptor, kind::f16: D = f32 (bit 4), A and B = f16 (0 at bits 7 and 10), b-negate bit 14,
 // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int b_neg) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_neg << 14) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int b_neg) {
+    return (1u << 4) | ((uint32_t)b_neg << 14) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // bounded wait (a lost completion traps instead of hanging the GPU)
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
@@ -88,26 +102,27 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 }
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TC_GROUP_THREADS) : "memory"); }
 
-// tensor-memory columns of one group (base = 256 * group)
-constexpr uint32_t COL_D = 0, COL_AHI_RE = 64, COL_AHI_IM = 96, COL_ALO_RE = 128, COL_ALO_IM = 160;
-constexpr uint32_t B_LBO = 128, B_SBO = 1024, B_IM_ROWS = 4 * B_SBO;     // rows 32..63 start 4 row groups in
+// tensor-memory columns of one group (base = 256 * group): D, then the hi and lo images of A.  In an image the thread
+// with top block bit h owns columns 16 h .. 16 h + 15: 8 of packed real parts (K chunk "Re, h"), 8 of imaginary parts
+constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 96;
+constexpr uint32_t B_LBO = 128, B_SBO = 512, B_IM_ROWS = 4 * B_SBO;      // rows 32..63 start 4 row groups in
 
-// all 36 instructions of one tile and sweep; `bimg` = shared-memory address of the slot's images (hi, then lo)
+// all 18 instructions of one tile and sweep; `bimg` = shared-memory address of the slot's images (hi, then lo)
 __device__ __forceinline__ void issue_block(uint32_t tbase, uint32_t bimg) {
-    constexpr uint32_t I64 = idesc_tf32(128, 64, 0), I32 = idesc_tf32(128, 32, 0), I32N = idesc_tf32(128, 32, 1);
+    constexpr uint32_t I64 = idesc_f16(128, 64, 0), I32 = idesc_f16(128, 32, 0), I32N = idesc_f16(128, 32, 1);
     const uint64_t hi = smem_desc(bimg, B_LBO, B_SBO), lo = smem_desc(bimg + TC_HALF_BYTES, B_LBO, B_SBO);
-    constexpr uint64_t KSTEP = (2 * B_LBO) >> 4, IM = B_IM_ROWS >> 4;
+    constexpr uint64_t KSTEP = (2 * B_LBO) >> 4, IM = B_IM_ROWS >> 4;     // 16 columns of U per instruction
     const uint32_t d = tbase + COL_D;
 #pragma unroll
     for (int term = 0; term < 3; ++term) {
-        const uint32_t are = tbase + (term == 0 ? COL_ALO_RE : COL_AHI_RE), aim = tbase + (term == 0 ? COL_ALO_IM : COL_AHI_IM);
+        const uint32_t a = tbase + (term == 0 ? COL_ALO : COL_AHI);
         const uint64_t b = term == 1 ? lo : hi;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma(d, are + 8 * ks, b + ks * KSTEP, I64, (term | ks) ? 1u : 0u);
+        for (int h = 0; h < 2; ++h) mma(d, a + 16 * h, b + h * KSTEP, I64, (term | h) ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma(d, aim + 8 * ks, b + IM + ks * KSTEP, I32N, 1u);
+        for (int h = 0; h < 2; ++h) mma(d, a + 16 * h + 8, b + IM + h * KSTEP, I32N, 1u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) mma(d + 32, aim + 8 * ks, b + ks * KSTEP, I32, 1u);
+        for (int h = 0; h < 2; ++h) mma(d + 32, a + 16 * h + 8, b + h * KSTEP, I32, 1u);
     }
 }
 
@@ -117,9 +132,12 @@ struct Ctx {
     uint32_t bimg0;        // shared-memory address of block-matrix slot 0
     uint64_t *bar;         // this group's completion barrier
     uint32_t phase;
+    float scale, inv_scale;   // power of two that ranges the fp16 operands, and its inverse
     int group, gtid;
 #ifdef QCS_TC_DBG
-    uint32_t dbg;          // timing experiments only (scratch builds): 1 no MMA, 2 no split / tcgen05.st, 4 no tcgen05.ld, 8 no tile LDS / STS
+    bool trace_on;
+    uint32_t trace_i;
+    uint32_t dbg;          // timing experiments only (scratch builds): 1 no MMA, 2 no split / tcgen05.st, 4 no tcgen05.ld, 8 no tile LDS / STS, 16 trivial addresses, 32 every warp polls, 64 no commit / wait (with 1), 128 no register ops, 256 no barriers around the MMA
 #endif
 };
 #ifdef QCS_TC_DBG
@@ -128,42 +146,44 @@ struct Ctx {
 #define TC_DBG(ctx, bit) false
 #endif
 
-// tf32 "hi" part: the 19 bits the tensor core reads (it ignores the low 13 mantissa bits); lo = x - hi is exact and
-// at most 2^-10 |x|, and ITS truncation to tf32 leaves 2^-20 |x| -- one AND + one subtraction per real number
-__device__ __forceinline__ uint32_t tf32_round(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+// two-term fp16 split of a pair of (scaled) reals: hi = fp16(v) (round to nearest), lo = fp16(v - hi); packed with
+// the first value in the low half (K even)
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 
 // One sweep of the tensor-core kernel: register ops (the generated interpreter), then -- if the sweep has a block --
 // the dense 2^5 x 2^5 matrix on tensor cores.  Thread (rho, h) of the group owns row rho of the tile and the 16
 // amplitudes whose top block bit is h.
 template <typename Layout>
-__device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp *rops, const float2 *pool, uint64_t outer_ok,
-                                      Ctx &ctx) {
+__device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const uint32_t *tab, const RegOp *rops, const float2 *pool,
+                                      uint64_t outer_ok, Ctx &ctx, bool first_touch) {
     constexpr int NX = 16;
     // the record as one 8-byte broadcast load; masks and strides are recomputed from the four register-bit positions
     // (a dozen integer ops) instead of being fetched with dependent shared-memory loads
+    TC_STAMP(ctx, 1);
     uint32_t plo, phi;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(plo), "=r"(phi) : "r"(smem_u32(&sw.packed)) : "memory");
-    const uint32_t rho = (uint32_t)ctx.gtid & 127u, h = (uint32_t)ctx.gtid >> 7, p = (plo >> 16) & 15u;
+    const uint32_t h = (uint32_t)ctx.gtid >> 7;
     const uint32_t flags = plo >> 24, first = phi;
     const int tc_slot = (int)((plo >> 20) & 15u) - 1;
-    uint32_t base = ((rho >> p) << (p + 1)) | (h << p) | (rho & ((1u << p) - 1u));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) base += base & (0xFFFFFFFFu << ((plo >> (4 * j)) & 15u));
+    // the thread's first amplitude (tile-local index, shared-memory byte offset) comes from the per-pass table built at
+    // kernel start -- it is the same for every tile -- and the four strides from the host-filled record
+    const uint32_t ent = tab[ctx.gtid];
+    const uint32_t base = ent >> 16;
     const bool VEC = (plo & 15u) == 0;
     uint32_t addr[NX];
-    if (TC_DBG(ctx, 16u)) {      // (timing experiment: trivial conflict-free addresses, no layout arithmetic)
-#pragma unroll
-        for (int x = 0; x < NX; ++x)
-            addr[x] = smem_u32(tile) + (VEC ? (uint32_t)((x >> 1) * 256 + ctx.gtid) * 16u + (uint32_t)(x & 1) * 8u
-                                            : (uint32_t)(x * 256 + ctx.gtid) * 8u);
-    } else {
-    addr[0] = smem_u32(tile) + Layout::amp(base) * (uint32_t)sizeof(float2);
+    uint32_t st4[4];
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(st4[0]), "=r"(st4[1]), "=r"(st4[2]), "=r"(st4[3]) : "r"(smem_u32(&sw.stride[0])) : "memory");
+    addr[0] = smem_u32(tile) + (ent & 0xFFFFu);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t st = Layout::amp(1u << ((plo >> (4 * j)) & 15u)) * (uint32_t)sizeof(float2);
 #pragma unroll
-        for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st;
-    }
+        for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st4[j];
     }
     float2 a[NX];
     if (TC_DBG(ctx, 8u)) {
@@ -179,7 +199,12 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
         for (int x = 0; x < NX; ++x)
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[x].x), "=f"(a[x].y) : "r"(addr[x]) : "memory");
     }
-    if (flags & 1u) {
+    if (first_touch) {     // the tile stays ranged (times s, a power of two) until the store-out folds 1 / s back in
+#pragma unroll
+        for (int x = 0; x < NX; ++x) { a[x].x *= ctx.scale; a[x].y *= ctx.scale; }
+    }
+    TC_STAMP(ctx, 2);      // tile in registers (loads issued)
+    if ((flags & 1u) && !TC_DBG(ctx, 128u)) {
         float2 ph = make_float2(1.0f, 0.0f);
         if (flags & 2u) run_sweep_ops_dense2(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
         else run_sweep_ops(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
@@ -188,29 +213,26 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
             for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
         }
     }
+    TC_STAMP(ctx, 3);      // register ops done
     if (tc_slot >= 0) {
         const uint32_t col = ctx.lane_addr + 16u * h;
         if (!TC_DBG(ctx, 2u)) {
-            uint32_t hi[NX], lo[NX];
+            uint32_t hi[NX], lo[NX];       // 8 columns of packed real parts, then 8 of imaginary parts
 #pragma unroll
-            for (int x = 0; x < NX; ++x) {
-                hi[x] = tf32_round(a[x].x);
-                lo[x] = __float_as_uint(a[x].x - __uint_as_float(hi[x]));
+            for (int x = 0; x < NX; x += 2) {
+                split2(a[x].x, a[x + 1].x, hi[x >> 1], lo[x >> 1]);
+                split2(a[x].y, a[x + 1].y, hi[8 + (x >> 1)], lo[8 + (x >> 1)]);
             }
-            st16(col + COL_AHI_RE, hi);
-            st16(col + COL_ALO_RE, lo);
-#pragma unroll
-            for (int x = 0; x < NX; ++x) {
-                hi[x] = tf32_round(a[x].y);
-                lo[x] = __float_as_uint(a[x].y - __uint_as_float(hi[x]));
-            }
-            st16(col + COL_AHI_IM, hi);
-            st16(col + COL_ALO_IM, lo);
+            st16(col + COL_AHI, hi);
+            st16(col + COL_ALO, lo);
         }
+        TC_STAMP(ctx, 4);  // split + tcgen05.st issued
         wait_st();
         fence_before();
-        group_sync(ctx.group);
-        if ((ctx.gtid >> 5) == 0) {
+        TC_STAMP(ctx, 5);  // stores complete
+        if (!TC_DBG(ctx, 256u)) group_sync(ctx.group);
+        TC_STAMP(ctx, 6);  // barrier passed
+        if ((ctx.gtid >> 5) == 0 && !TC_DBG(ctx, 64u)) {
             // only this warp watches the completion barrier; the other seven sleep in the group barrier below
             // (a spinning try_wait loop in every warp took issue slots from the other group's register work)
             fence_after();
@@ -219,12 +241,15 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
                 commit(ctx.bar);
             }
             __syncwarp();
+            TC_STAMP(ctx, 7);  // MMAs issued
             mbar_wait_bounded(ctx.bar, ctx.phase);
+            TC_STAMP(ctx, 8);  // MMAs complete
         }
-        ctx.phase ^= 1u;
+        if (!TC_DBG(ctx, 64u)) ctx.phase ^= 1u;
         if (TC_DBG(ctx, 32u)) { if ((ctx.gtid >> 5) != 0) mbar_wait_bounded(ctx.bar, ctx.phase ^ 1u); }   // every warp watches the barrier itself
-        else group_sync(ctx.group);
+        else if (!TC_DBG(ctx, 256u)) group_sync(ctx.group);
         fence_after();
+        TC_STAMP(ctx, 9);  // second barrier passed
         if (!TC_DBG(ctx, 4u)) {
             uint32_t re[NX], im[NX];
             ld16(col + COL_D, re);
@@ -234,6 +259,7 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
             for (int x = 0; x < NX; ++x) { a[x].x = __uint_as_float(re[x]); a[x].y = __uint_as_float(im[x]); }
         }
         fence_before();        // orders these tensor-memory reads before the next sweep's barrier + MMA
+        TC_STAMP(ctx, 10); // D in registers
     }
     if (TC_DBG(ctx, 8u)) {
         if (a[3].x == 12345.678f) tile[0] = a[5];       // keep the values alive
@@ -248,6 +274,7 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const RegOp
         for (int x = 0; x < NX; ++x)
             asm volatile("st.shared.v2.f32 [%2], {%0, %1};" ::"f"(a[x].x), "f"(a[x].y), "r"(addr[x]) : "memory");
     }
+    TC_STAMP(ctx, 11);     // tile stores issued
 }
 
 }  // namespace tc
@@ -274,8 +301,20 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         top_off[j] = (1ull << (i < P.L ? i : P.hbits[i - P.L])) >> 1;
     }
     (void)chunk_off;
+    // per-sweep, per-thread addressing table: (tile-local index of the thread's first amplitude) << 16 | its byte offset in
+    // a stage.  Thread (rho, h) of a group owns row rho; h is inserted at rank `hrank` among the 8 thread bits and a zero
+    // at each of the four register-bit positions.
+    uint32_t *swtab = reinterpret_cast<uint32_t *>(smem_all + prog_bytes);
+    for (uint32_t i = tid; i < (uint32_t)P.nsweeps * NT; i += 2 * NT) {
+        const Sweep &sw = P.sweeps[i / NT];
+        if (sw.kind != SWEEP_REG) continue;
+        const uint32_t t = i % NT, rho = t & 127u, hh = t >> 7, p = (uint32_t)sw.hrank;
+        uint32_t base = ((rho >> p) << (p + 1)) | (hh << p) | (rho & ((1u << p) - 1u));
+        for (int j = 0; j < 4; ++j) base += base & (0xFFFFFFFFu << sw.rpos[j]);
+        swtab[i] = (base << 16) | (Layout::amp(base) * (uint32_t)sizeof(float2));
+    }
     // block-matrix images
-    unsigned char *bimg = smem_all + prog_bytes;
+    unsigned char *bimg = smem_all + prog_bytes + (size_t)P.nsweeps * NT * sizeof(uint32_t);
     {
         const uint4 *srcm = reinterpret_cast<const uint4 *>(P.tc_mats);
         uint4 *dstm = reinterpret_cast<uint4 *>(bimg);
@@ -298,17 +337,28 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     ctx.tbase = tmem_slot + 256u * (uint32_t)g;
     ctx.lane_addr = ctx.tbase + ((uint32_t)(((gtid >> 5) & 3) * 32) << 16);
     ctx.bimg0 = smem_u32(bimg);
+    {
+        // s = 2^(15 - e) with sqrt(norm^2) = m 2^e, m in [0.5, 1): every |s a| < 2^15 (fp16 holds 65504)
+        int e = 0;
+        const double n2 = P.tc_norm ? *P.tc_norm : 1.0;
+        if (n2 > 0.0 && n2 < 1e300) (void)frexp(sqrt(n2), &e);
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        ctx.scale = exp2f((float)(15 - e));
+        ctx.inv_scale = exp2f((float)(e - 15));
+    }
 #ifdef QCS_TC_DBG
     ctx.dbg = (uint32_t)P.tc_pad;
+    ctx.trace_on = false; ctx.trace_i = 0;
 #endif
 
     const int L = P.L;
     const uint32_t stage_bytes = (uint32_t)Layout::bytes(MT);
     const uint32_t svec_tid = Layout::vec((uint32_t)gtid);
-    const int scale_mode = P.scale_mode;
-    float fr = 1.0f, fi = 0.0f;
-    if (scale_mode) {
-        const double s = load_inv_norm(P.norm_in);
+    // the store-out always multiplies: lazy norm / global phase of the pass, and 1 / s of the fp16 ranging
+    const int scale_mode = P.scale_mode == 2 ? 2 : 1;
+    float fr = ctx.inv_scale, fi = 0.0f;
+    if (P.scale_mode) {
+        const double s = load_inv_norm(P.norm_in) * (double)ctx.inv_scale;
         fr = (float)(s * P.gphase[0]); fi = (float)(s * P.gphase[1]);
     }
     uint64_t low_tid = 0;
@@ -324,8 +374,10 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     const uint64_t my_tiles = (P.ntiles > vcta) ? (P.ntiles - 1 - vcta) / vgrid + 1 : 0;
     const float2 *pool = reinterpret_cast<const float2 *>(pv.pool);
 
+    uint64_t next_base = 0;            // flat index of the tile whose copies were issued last (computed once per tile)
     auto issue_load = [&](uint64_t it, int st) {
         const uint64_t base = tile_base_of(vcta + it * vgrid, P);
+        next_base = base;
         const uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
@@ -337,21 +389,36 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     cp_async_commit();
     int st = 0;
     for (uint64_t it = 0; it < my_tiles; ++it) {
-        const uint64_t base = tile_base_of(vcta + it * vgrid, P);
+        const uint64_t base = next_base;
         const int parity = (int)(it & 1) + 2 * g;
+#ifdef QCS_TC_DBG
+        ctx.trace_on = tid == 0 && blockIdx.x == 0 && it >= 100 && it < 104;
+#endif
+        TC_STAMP(ctx, 20);
         eval_outer(pv, base, parity, gtid);
         cp_async_wait_pending(0);          // this thread's copies of tile `it` have landed
+        TC_STAMP(ctx, 21);
         tc::group_sync(g);                 // ... everyone's have, and the other stage is drained
+        TC_STAMP(ctx, 22);
+        // (issuing the next tile's copies later -- while the tensor core works on this tile's first block -- was measured
+        // slower: 202 vs 182 ms on the headline circuit)
         if (it + 1 < my_tiles) issue_load(it + 1, st ^ 1);
         cp_async_commit();
         unsigned char *stage = ring + (size_t)st * stage_bytes;
         const uint64_t outer_ok = (pv.nouter ? pv.outer_ok[parity] : 0ull) | (1ull << OUTER_SLOT_NONE);
+        bool ranged = false;
         for (int s = 0; s < pv.nsweeps; ++s) {
+            if (TC_DBG(ctx, 512u)) break;                          // (timing experiment: staging and store-out only)
             const Sweep &sw = pv.sweeps[s];
-            if (sw.kind == SWEEP_REG) tc::sweep<Layout>(reinterpret_cast<C *>(stage), sw, pv.regops, pool, outer_ok, ctx);
+            if (sw.kind == SWEEP_REG) {
+                tc::sweep<Layout>(reinterpret_cast<C *>(stage), sw, swtab + s * NT, pv.regops, pool, outer_ok, ctx, !ranged);
+                ranged = true;
+            }
             else apply_generic<float, Layout>(reinterpret_cast<C *>(stage), MT, pv.gen[sw.first], pool, base, gtid, NT);
             tc::group_sync(g);
+            TC_STAMP(ctx, 12);     // end-of-sweep barrier passed
         }
+        TC_STAMP(ctx, 23);
         float tacc = 0.0f;
         const uint4 *sbase = reinterpret_cast<const uint4 *>(stage) + svec_tid;
 #pragma unroll
@@ -364,8 +431,12 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         }
         nacc[0] += (double)tacc;
         st ^= 1;
+        TC_STAMP(ctx, 24);         // store-out issued
     }
     cp_async_wait_pending(0);
+#ifdef QCS_TC_DBG
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace_n = ctx.trace_i;
+#endif
     tc::fence_before();
     __syncthreads();
     if (tid < 32) tc::tmem_dealloc(tmem_slot, 512);

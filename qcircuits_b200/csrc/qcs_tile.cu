@@ -808,18 +808,44 @@ static thread_local int32_t *g_sweep_of_op = nullptr;           // set by tile_p
 static thread_local unsigned char *g_block_dump = nullptr;     // set by tile_plan_blocks (diagnostics / tests)
 static thread_local int32_t *g_block_info = nullptr;
 
-static inline float tf32_round_host(float x) {          // nearest, ties away: what cvt.rna.tf32.f32 does
-    uint32_t u;
-    std::memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;
-    float r;
-    std::memcpy(&r, &u, 4);
-    return r;
+// round to nearest even, to fp16 and back / the 16 bits (host)
+static inline uint16_t half_bits_host(float x) {
+    const __half h = __float2half_rn(x);
+    uint16_t u;
+    std::memcpy(&u, &h, 2);
+    return u;
+}
+static inline float half_value_host(float x) { return __half2float(__float2half_rn(x)); }
+
+// Is the op a unitary (within 1e-4, entry-wise on U^H U - 1)?  The tensor-core kernel ranges its fp16 operands with the
+// norm of the state, which only unitaries keep; anything else runs on the register-sweep kernel in fp32.
+static bool op_is_unitary(const qcs_op &o) {
+    const int dim = 1 << o.k;
+    const double tol = 1e-4;
+    if (o.kind == QCS_OP_DIAG) {
+        for (int y = 0; y < dim; ++y) {
+            const double m2 = o.matrix[2 * y] * o.matrix[2 * y] + o.matrix[2 * y + 1] * o.matrix[2 * y + 1];
+            if (!(std::fabs(m2 - 1.0) <= tol)) return false;
+        }
+        return true;
+    }
+    for (int a = 0; a < dim; ++a)
+        for (int b = a; b < dim; ++b) {
+            double sr = 0.0, si = 0.0;                    // sum_y conj(U[y][a]) U[y][b]
+            for (int y = 0; y < dim; ++y) {
+                const double ar = o.matrix[2 * (y * dim + a)], ai = o.matrix[2 * (y * dim + a) + 1];
+                const double br = o.matrix[2 * (y * dim + b)], bi = o.matrix[2 * (y * dim + b) + 1];
+                sr += ar * br + ai * bi;
+                si += ar * bi - ai * br;
+            }
+            if (!(std::fabs(sr - (a == b ? 1.0 : 0.0)) <= tol) || !(std::fabs(si) <= tol)) return false;
+        }
+    return true;
 }
 
 // Product of the listed ops (in order) as a 2^5 x 2^5 complex matrix over the block index, written as the two
-// shared-memory images of a slot (qcs_tc.cuh: K-major, no swizzle; rows 0..31 = Re U, rows 32..63 = Im U; "hi"
-// image = tf32(U), "lo" image = tf32(U - hi)).  block_bit(flat bit) = bit of the block index that flat bit maps to.
+// shared-memory images of a slot (qcs_tc.cuh: fp16, K-major, no swizzle; rows 0..31 = Re U, rows 32..63 = Im U; "hi"
+// image = fp16(U), "lo" image = fp16(U - hi)).  block_bit(flat bit) = bit of the block index that flat bit maps to.
 template <typename F>
 static void tc_build_block(const qcs_op *ops, const int *list, int count, F block_bit, unsigned char *image) {
     constexpr int D = 1 << TC_BLOCK_BITS;
@@ -864,16 +890,18 @@ static void tc_build_block(const qcs_op *ops, const int *list, int count, F bloc
             }
         }
     }
-    float *hi = reinterpret_cast<float *>(image), *lo = reinterpret_cast<float *>(image + TC_HALF_BYTES);
+    // element (row n, column k) of an image sits at (n % 8) * 16 + (n / 8) * 512 + (k / 8) * 128 + (k % 8) * 2 bytes:
+    // 8 x 16-byte core matrices, LBO = 128 bytes between the K chunks, SBO = 512 bytes between the 8-row groups
+    uint16_t *hi = reinterpret_cast<uint16_t *>(image), *lo = reinterpret_cast<uint16_t *>(image + TC_HALF_BYTES);
     for (int part = 0; part < 2; ++part)
         for (int r = 0; r < D; ++r)
             for (int c = 0; c < D; ++c) {
                 const int nrow = part * D + r;
-                const size_t off = ((size_t)(nrow % 8) * 16 + (size_t)(nrow / 8) * 1024 + (size_t)(c / 4) * 128 + (size_t)(c % 4) * 4) / 4;
+                const size_t off = ((size_t)(nrow % 8) * 16 + (size_t)(nrow / 8) * 512 + (size_t)(c / 8) * 128 + (size_t)(c % 8) * 2) / 2;
                 const double v = U[r][c][part];
-                const float h = tf32_round_host((float)v);
-                hi[off] = h;
-                lo[off] = tf32_round_host((float)(v - (double)h));
+                const float h = half_value_host((float)v);
+                hi[off] = half_bits_host((float)v);
+                lo[off] = half_bits_host((float)(v - (double)h));
             }
 }
 
@@ -918,7 +946,8 @@ static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
             return set_error(QCS_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
         if (device < 64) attr_done[device] = true;
     }
-    const size_t smem = program_smem_bytes(P) + (size_t)P.n_tc * TC_SLOT_BYTES + 2 * TC_STAGES * Layout::bytes(TILE_MIN_BITS_C64);
+    const size_t smem = program_smem_bytes(P) + (size_t)P.nsweeps * TC_GROUP_THREADS * sizeof(uint32_t) + (size_t)P.n_tc * TC_SLOT_BYTES +
+                        2 * TC_STAGES * Layout::bytes(TILE_MIN_BITS_C64);
     if (smem > (size_t)SMEM_LIMIT) return set_error(QCS_ERR_UNSUPPORTED, "tensor-core pass does not fit shared memory");
     P.stages = TC_STAGES;
     uint64_t grid = (uint64_t)dev.sms;
@@ -937,7 +966,7 @@ static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
 template <typename Prog>
 static int build_and_launch(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops,
                             const double *norm_in, double *norm_out, void *ws, cudaStream_t stream,
-                            int32_t *stats = nullptr) {
+                            int32_t *stats = nullptr, const double *bound_in = nullptr) {
     const bool c64 = dtype == QCS_C64;
     const int vshift = c64 ? 1 : 0;
     Prog *Pp = new Prog();
@@ -1015,8 +1044,11 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
     constexpr bool TCPROG = std::is_same<Prog, TcProg>::value;
     const bool use_tc = TCPROG && c64 && m == TILE_MIN_BITS_C64 && n >= TILE_MIN_BITS_C64 && tune_int("QCS_TC", 1) != 0;
     if (TCPROG && !use_tc) return set_error(QCS_ERR_UNSUPPORTED, "not a tensor-core pass");
-    int tc_max_slots = tune_int("QCS_TC_SLOTS", TC_MAX_SLOTS);
+    int tc_max_slots = tune_int("QCS_TC_SLOTS", TC_DEFAULT_SLOTS);
     if (tc_max_slots > TC_MAX_SLOTS) tc_max_slots = TC_MAX_SLOTS;
+    if (TCPROG)
+        for (int i = 0; i < nops; ++i)
+            if (!op_is_unitary(ops[i])) return set_error(QCS_ERR_UNSUPPORTED, "non-unitary op: not a tensor-core pass");
     static thread_local unsigned char tc_images[TC_MAX_SLOTS * TC_SLOT_BYTES];
     int tc_block_ops = 0;
     uint32_t op_lmask[QCS_MAX_OPS];        // tile-local mask of every bit the op touches inside the tile
@@ -1027,7 +1059,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         op_lmask[i] = local_mask(all & tile_mask);
         op_inside[i] = (all & ~tile_mask) == 0 && __builtin_popcountll(all) <= TC_BLOCK_BITS;
     }
-    P.n_tc = 0; P.tc_mats = nullptr; P.tc_pad = tune_int("QCS_TC_DEBUG", 0);   // (read by scratch builds with -DQCS_TC_DBG only)
+    P.n_tc = 0; P.tc_mats = nullptr; P.tc_norm = nullptr; P.tc_pad = tune_int("QCS_TC_DEBUG", 0);   // (read by scratch builds with -DQCS_TC_DBG only)
 
     // ---- matrix pool -----------------------------------------------------------------------------------
     const size_t csize = c64 ? 8 : 16;
@@ -1543,6 +1575,14 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
         const int rc = tc_upload(tc_images, P.n_tc, ws, stream);
         if (rc != QCS_OK) return rc;
         P.tc_mats = reinterpret_cast<const unsigned char *>(ws) + WS_TC_OFFSET;
+        // the fp16 operands are ranged with the norm of the state: the caller's lazy norm, its bound, or one reduction here
+        P.tc_norm = bound_in ? bound_in : norm_in;
+        if (!P.tc_norm) {
+            double *scratch = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ws) + WS_TC_NORM_OFFSET);
+            const int rn = misc_abs2(nullptr, src, n, dtype, nullptr, scratch, ws, stream);
+            if (rn != QCS_OK) return rn;
+            P.tc_norm = scratch;
+        }
         return launch_tc(P, dev, stream);
     } else {
         const int mode = tile_mode();
@@ -1551,7 +1591,7 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
 }
 
 int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, int nops, const double *norm_in,
-               double *norm_out, void *ws, cudaStream_t stream) {
+               double *norm_out, const double *bound_in, void *ws, cudaStream_t stream) {
     if (nops < 1) return set_error(QCS_ERR_ARG, "empty op list");
     // Alternative for a pass that is one one-qubit gate: stream straight through registers with strided 128-bit
     // loads, no shared-memory tile (qcs_misc.cu: gate1_stream_kernel).  Parity-green but measured SLOWER than the
@@ -1568,7 +1608,7 @@ int tile_apply(void *dst, const void *src, int n, int dtype, const qcs_op *ops, 
     }
     if (dtype == QCS_C64 && ws && n >= TILE_MIN_BITS_C64 && nops >= tune_int("QCS_TC_MIN_OPS", 3)) {
         // passes with dense blocks run on the tensor-core kernel (the planner says "unsupported" when it finds none)
-        const int rc = build_and_launch<TcProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
+        const int rc = build_and_launch<TcProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream, nullptr, bound_in);
         if (rc != QCS_ERR_UNSUPPORTED) return rc;
     }
     return build_and_launch<LargeProg>(dst, src, n, dtype, ops, nops, norm_in, norm_out, ws, stream);
@@ -1603,3 +1643,15 @@ int tile_plan_blocks(int n, const qcs_op *ops, int nops, int32_t *stats, void *i
 }
 
 }  // namespace qcs
+
+#ifdef QCS_TC_DBG
+// timing experiments only (scratch builds): the clock stamps of the last tensor-core launch
+extern "C" int qcs_debug_tc_trace(unsigned long long *out, int max_pairs) {
+    unsigned int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, qcs::g_tc_trace_n, sizeof n);
+    if ((int)n > max_pairs) n = (unsigned)max_pairs;
+    cudaMemcpyFromSymbol(out, qcs::g_tc_trace, (size_t)n * 16);
+    return (int)n;
+}
+#endif

@@ -1,5 +1,5 @@
-"""Tensor-core sweeps (tile_kernel_tc: tcgen05.mma kind::tf32, 3-term split, accumulators in tensor memory)
-against the oracle.  complex64 only; the bar is the north star's 1e-5 relative to the largest amplitude."""
+"""Tensor-core sweeps (tile_kernel_tc: tcgen05.mma kind::f16, two-term fp16 split of both operands, accumulators in
+tensor memory) against the oracle.  complex64 only; the bar is the north star's 1e-5 relative to the largest amplitude."""
 import ctypes
 
 import numpy as np
@@ -127,18 +127,61 @@ def test_tensor_core_pass_equals_register_pass(monkeypatch):
     assert rel_err(got_tc, got_reg) < TOL
 
 
-def test_non_unitary_block_and_lazy_norm():
-    """a block is whatever the product of the gates is: projectors and arbitrary matrices renormalise as in the
-    reference (operators.py:275-276) through the squared norm the pass emits"""
+def test_non_unitary_ops_stay_off_the_tensor_cores_and_lazy_norm():
+    """the fp16 operands are ranged with the norm of the state, which only unitaries keep: a pass with a projector or an
+    arbitrary matrix runs on the register-sweep kernel (fp32) and renormalises as in the reference
+    (operators.py:275-276) through the squared norm the pass emits; the same pass with unitaries takes the tensor cores"""
     rng = np.random.default_rng(4)
     n = 15
     vec = rand_state_vec(rng, n)
     gates = [(rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)), [3]), (CNOT, [3, 4]),
              (np.array([[1, 0], [0, 0]], dtype=np.complex128), [5]), (rand_unitary(rng, 2), [4, 6]), (H, [7])]
     got, want, st = _run(n, vec, gates)
+    assert st[7] & 255 == 0
+    assert rel_err(got, want) < TOL
+    assert abs(np.vdot(got, got) - 1.0) < 1e-5
+    gates[0] = (rand_unitary(rng, 1), [3])
+    gates[2] = (_rz(0.7), [5])
+    got, want, st = _run(n, vec, gates)
     assert st[7] & 255 >= 1
     assert rel_err(got, want) < TOL
     assert abs(np.vdot(got, got) - 1.0) < 1e-5
+
+
+def test_ranging_of_the_fp16_operands():
+    """states whose norm is far from one (the caller gave no lazy norm: the library measures it), a basis state (one
+    amplitude carries everything) and a state that is tiny almost everywhere: the error bar stays relative to the
+    largest amplitude"""
+    rng = np.random.default_rng(9)
+    n = 16
+    gates = []
+    for _ in range(24):
+        a, b = (int(v) for v in rng.choice(5, size=2, replace=False))
+        gates.append((rand_unitary(rng, 2), [3 + a, 3 + b]))
+    lib = _lib.load()
+    plans = [(_gates.analyze(M), bits, False) for M, bits in gates]
+    ops, keep = make_ops(plans)
+    stats = (ctypes.c_int32 * 128)()
+    _lib.check(lib.qcs_plan_stats(n, _lib.QCS_C64, ops, len(ops), stats))
+    assert stats[7] & 255 >= 1
+    t = _lib.torch()
+    basis = np.zeros(2 ** n, dtype=np.complex128)
+    basis[12345] = 1.0
+    spiky = rand_state_vec(rng, n) * 1e-6
+    spiky[777] = 0.8
+    for name, vec in (('x 1e-12', rand_state_vec(rng, n) * 1e-12), ('x 3e8', rand_state_vec(rng, n) * 3e8),
+                      ('basis state', basis), ('one large amplitude', spiky)):
+        want = vec.copy()
+        for M, bits in gates:
+            want = orc.apply_matrix_flat(M, want, bits, renorm=False)
+        buf = t.from_numpy(vec.astype(np.complex64).view(np.float32)).cuda()
+        ws = _lib.workspace()
+        _lib.check(lib.qcs_apply_fused(buf.data_ptr(), buf.data_ptr(), n, _lib.QCS_C64, ops, len(ops), None, None,
+                                       ws.data_ptr(), _lib.stream_ptr()))
+        got = buf.cpu().numpy().view(np.complex64).astype(np.complex128)
+        err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+        print('%s: error / tolerance %.3f' % (name, err / TOL))
+        assert err < TOL, name
 
 
 def test_layered_circuit_through_the_scheduler():
