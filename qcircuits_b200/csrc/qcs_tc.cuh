@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     uint64_t top_off[3];
     for (int j = 0; j < 3; ++j) {
         const int i = TILE_MIN_BITS_C64 - 3 + j;
-        top_off[j] = (1ull << (i < P.L ? i : P.hbits[i - P.L])) >> 1;
+        top_off[j] = (1ull << (i < P.L ? i : P.hbits[i - P.L])) * sizeof(float2);      // in bytes
     }
     (void)chunk_off;
     // per-sweep, per-thread addressing table: (tile-local index of the thread's first amplitude) << 16 | its byte offset in
@@ -379,10 +379,17 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         const uint64_t base = tile_base_of(vcta + it * vgrid, P);
         next_base = base;
         const uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
+        // the 8 vectors of a thread: one pointer + the three top-bit offsets (7 additions, no per-vector index arithmetic)
+        const unsigned char *gptr[NK];
+        gptr[0] = reinterpret_cast<const unsigned char *>(src) + base * sizeof(float2);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int k = 0; k < (1 << j); ++k) gptr[k | (1 << j)] = gptr[k] + top_off[j];
+        }
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            const uint4 *gp = src + ((base >> VSHIFT) + ((k & 1) ? top_off[0] : 0ull) + ((k & 2) ? top_off[1] : 0ull) + ((k & 4) ? top_off[2] : 0ull));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp + Layout::vec((uint32_t)(k * NT)) * 16u), "l"(gp) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp + Layout::vec((uint32_t)(k * NT)) * 16u), "l"(gptr[k]) : "memory");
         }
     };
     if (my_tiles > 0) issue_load(0, 0);
@@ -421,13 +428,20 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         TC_STAMP(ctx, 23);
         float tacc = 0.0f;
         const uint4 *sbase = reinterpret_cast<const uint4 *>(stage) + svec_tid;
+        unsigned char *optr[NK];
+        optr[0] = reinterpret_cast<unsigned char *>(dst) + base * sizeof(float2);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int k = 0; k < (1 << j); ++k) optr[k | (1 << j)] = optr[k] + top_off[j];
+        }
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
             uint4 val = sbase[Layout::vec((uint32_t)(k * NT))];
             if (scale_mode == 1) val = vec_scale<float>(val, fr);
             else if (scale_mode == 2) val = vec_cscale<float>(val, fr, fi);
             vec_norm_acc(tacc, val, 0.0f);
-            dst[(base >> VSHIFT) + ((k & 1) ? top_off[0] : 0ull) + ((k & 2) ? top_off[1] : 0ull) + ((k & 4) ? top_off[2] : 0ull)] = val;
+            *reinterpret_cast<uint4 *>(optr[k]) = val;
         }
         nacc[0] += (double)tacc;
         st ^= 1;

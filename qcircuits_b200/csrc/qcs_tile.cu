@@ -1157,11 +1157,12 @@ static int build_and_launch(void *dst, const void *src, int n, int dtype, const 
                 return first_taken;
             };
             // candidate bits: the tile bits of the first pending ops, in order of appearance
-            int W[10], nW = 0;
+            int W[16], nW = 0;
             uint32_t Wmask = 0;
-            for (int i = 0; i < npend && i < 48 && nW < 9; ++i) {
+            const int cand_bits = tune_int("QCS_TC_CAND_BITS", 9), cand_ops = tune_int("QCS_TC_CAND_OPS", 48);
+            for (int i = 0; i < npend && i < cand_ops && nW < cand_bits; ++i) {
                 const uint32_t lm = op_lmask[pending[i]];
-                for (int b = 0; b < m && nW < 9; ++b)
+                for (int b = 0; b < m && nW < cand_bits; ++b)
                     if (((lm >> b) & 1u) && !((Wmask >> b) & 1u)) { W[nW++] = b; Wmask |= 1u << b; }
             }
             for (int b = m - 1; b >= 0 && nW < TC_BLOCK_BITS; --b)      // fewer than five wanted bits: pad

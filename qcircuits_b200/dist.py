@@ -175,6 +175,21 @@ def specialize(plan, bits, n_local, rank):
     return new_plan, [bits[q] for q in used]
 
 
+def _all_unitary(circuit):
+    """every gate of the circuit is a unitary (cached on the circuit per gate count)"""
+    key = len(circuit.gates)
+    hit = circuit.__dict__.get('_unitary_cache')
+    if hit is None or hit[0] != key:
+        ok = True
+        for gt in circuit.gates:
+            M = gt.plan.full
+            if M is None or np.abs(M.conj().T @ M - np.eye(M.shape[0])).max() > 1e-6:
+                ok = False
+                break
+        hit = circuit.__dict__['_unitary_cache'] = (key, ok)
+    return hit[1]
+
+
 class _LogicalGate:
     __slots__ = ('plan', 'qubits')
 
@@ -224,6 +239,9 @@ class CudaEngine:
         self.spare = self._alloc_shard(n_local)
         self.launches = 0
         self.exchange_kind = None
+        # device scalar >= the squared norm of the WHOLE state (None: not known): ranges the fp16 operands of the
+        # tensor-core sweeps (qcs_apply_fused_bounded) so that no pass has to measure its shard
+        self.bound2 = None
 
     def _alloc_shard(self, n_local):
         if not self._p2p:
@@ -244,6 +262,7 @@ class CudaEngine:
             self.buf.zero_()
         else:
             _lib.check(lib.qcs_set_basis(self.buf.data_ptr(), self.n_local, self.code, index, _lib.stream_ptr()))
+        self.bound2 = _lib.torch().ones(2, dtype=_lib.torch().float64, device='cuda')     # a basis state: norm 1
 
     def compile_local(self, rank_gates, max_ops):
         """schedule + plan the fused passes of a communication-free step once (ShardedState.run caches the result)"""
@@ -254,9 +273,10 @@ class CudaEngine:
     def run_compiled(self, passes):
         lib = _lib.load()
         ws = _lib.workspace().data_ptr()
+        bound = None if self.bound2 is None else self.bound2.data_ptr()
         for ops, keep, _ in passes:
-            _lib.check(lib.qcs_apply_fused(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, ops,
-                                           len(ops), None, None, ws, _lib.stream_ptr()))
+            _lib.check(lib.qcs_apply_fused_bounded(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, ops,
+                                                   len(ops), None, None, bound, ws, _lib.stream_ptr()))
             self.launches += 1
 
     def run_local(self, rank_gates, max_ops):
@@ -367,16 +387,19 @@ class CudaEngine:
     def load_host(self, vec):
         """this rank's 2^n_local amplitudes from a host array"""
         self.buf.copy_(_lib.upload(np.asarray(vec).reshape(-1), self.dtype))
+        self.bound2 = None
 
     def to_host(self):
         return _lib.download(self.buf, self.dtype).astype(np.complex128)
 
     def zero(self):
         self.buf.zero_()
+        self.bound2 = None
 
     def scale(self, factor):
         _lib.check(_lib.load().qcs_scale(self.buf.data_ptr(), self.buf.data_ptr(), self.n_local, self.code, float(factor), 0.0,
                                          None, None, None, _lib.stream_ptr()))
+        self.bound2 = None
 
     def collapse(self, bitpos, outcome, remove, scale):
         """keep the amplitudes whose bits at bitpos equal outcome, times scale (qcs_collapse); remove drops those bits"""
@@ -395,6 +418,7 @@ class CudaEngine:
         else:
             self.buf, self.spare = self.spare, self.buf
         self.launches += 1
+        self.bound2 = None
 
     def kron_low(self, vec):
         """shard <- shard (x) vec: the new qubits become the lowest physical bits (qcs_kron)"""
@@ -409,10 +433,12 @@ class CudaEngine:
         self.n_local += nb
         self.buf = dst
         self.spare = self._alloc_shard(self.n_local)
+        self.bound2 = None
 
     def clone(self):
         other = CudaEngine(self.n_local, self.dtype)
         other.buf.copy_(self.buf)
+        other.bound2 = None if self.bound2 is None else self.bound2.clone()
         return other
 
     def marginals(self, bitpos):
@@ -485,6 +511,7 @@ class ShardedState:
                     compiled.append(step)
             plan = cache[key] = (compiled, phys, circuit)          # (the circuit is kept alive: its id is the key)
         compiled, phys, _ = plan
+        self._ensure_bound()
         for step in compiled:
             if step[0] == 'passes':
                 self.engine.run_compiled(step[1])
@@ -497,7 +524,20 @@ class ShardedState:
                 self.exchanges += 1
         self.phys = list(phys)
         self.norm = None
+        if getattr(self.engine, 'bound2', None) is not None and not _all_unitary(circuit):
+            self.engine.bound2 = None              # the norm has changed: measured again before the next run
         return self
+
+    def _ensure_bound(self):
+        """the squared norm of the whole state as a device scalar on the engine (one reduction + all-reduce when it is not
+        known; unitary circuits keep it): libqcs ranges the fp16 tensor-core operands with it"""
+        eng = self.engine
+        if not hasattr(eng, 'bound2') or eng.bound2 is not None:
+            return
+        import torch.distributed as dist
+        part = eng.norm2().clone()
+        dist.all_reduce(part, group=self.group)
+        eng.bound2 = part.repeat(2)
 
     # -- construction / export ------------------------------------------------------------------------------------
     @property
