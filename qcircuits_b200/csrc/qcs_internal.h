@@ -106,8 +106,7 @@ constexpr int TC_HALF_BYTES = 64 * 32 * 2;           // one fp16 image: rows 0..
 constexpr int TC_SLOT_BYTES = 2 * TC_HALF_BYTES;     // "hi" image = fp16(U), then the "lo" image = fp16(U - hi)
 constexpr int TC_DEFAULT_SLOTS = 6;                  // what the planner uses unless QCS_TC_SLOTS says otherwise
 constexpr int64_t WS_TC_NORM_OFFSET = 32640;         // squared norm of src when the caller gave none (tile_apply computes it)
-constexpr int TC_GROUP_THREADS = 256;                // two groups per CTA, each streams its own tiles
-constexpr int TC_STAGES = 2;                         // ring stages per group
+constexpr int TC_DEFAULT_GROUPS = 4;                 // groups per CTA (2 x 256 threads with two ring stages each, or 4 x 128 with one)
 constexpr int64_t WS_TC_OFFSET = 32768;              // block-matrix images live in the caller's workspace from here
 constexpr int TC_UPLOAD_RING = 8;                    // pinned host staging sets for their upload (one per launch in flight)
 static_assert(sizeof(Sweep) % 16 == 0 && offsetof(Sweep, packed) % 8 == 0 && offsetof(Sweep, stride) % 16 == 0,

@@ -100,9 +100,10 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
     }
     asm volatile("trap;");
 }
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TC_GROUP_THREADS) : "memory"); }
+template <int GT>
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory"); }
 
-// tensor-memory columns of one group (base = 256 * group): D, then the hi and lo images of A.  In an image the thread
+// tensor-memory columns of one group (base = (512 / groups) * group): D, then the hi and lo images of A.  In an image the thread
 // with top block bit h owns columns 16 h .. 16 h + 15: 8 of packed real parts (K chunk "Re, h"), 8 of imaginary parts
 constexpr uint32_t COL_D = 0, COL_AHI = 64, COL_ALO = 96;
 constexpr uint32_t B_LBO = 128, B_SBO = 512, B_IM_ROWS = 4 * B_SBO;      // rows 32..63 start 4 row groups in
@@ -157,99 +158,132 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t &hi, uint32_
 }
 
 // One sweep of the tensor-core kernel: register ops (the generated interpreter), then -- if the sweep has a block --
-// the dense 2^5 x 2^5 matrix on tensor cores.  Thread (rho, h) of the group owns row rho of the tile and the 16
-// amplitudes whose top block bit is h.
-template <typename Layout>
+// the dense 2^5 x 2^5 matrix on tensor cores.  A row of the tile (32 amplitudes) is two "virtual threads" (rho, h), each
+// owning the 16 amplitudes whose top block bit is h: with 256-thread groups (HALVES = 1) they are two threads, with
+// 128-thread groups (HALVES = 2) thread rho does both, one after the other.
+template <typename Layout, int HALVES>
 __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const uint32_t *tab, const RegOp *rops, const float2 *pool,
                                       uint64_t outer_ok, Ctx &ctx, bool first_touch) {
     constexpr int NX = 16;
-    // the record as one 8-byte broadcast load; masks and strides are recomputed from the four register-bit positions
-    // (a dozen integer ops) instead of being fetched with dependent shared-memory loads
+    constexpr int GT = 256 / HALVES;
+    // the record as one 8-byte broadcast load, the four register-bit strides as one 16-byte load
     TC_STAMP(ctx, 1);
     uint32_t plo, phi;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(plo), "=r"(phi) : "r"(smem_u32(&sw.packed)) : "memory");
-    const uint32_t h = (uint32_t)ctx.gtid >> 7;
     const uint32_t flags = plo >> 24, first = phi;
     const int tc_slot = (int)((plo >> 20) & 15u) - 1;
-    // the thread's first amplitude (tile-local index, shared-memory byte offset) comes from the per-pass table built at
-    // kernel start -- it is the same for every tile -- and the four strides from the host-filled record
-    const uint32_t ent = tab[ctx.gtid];
-    const uint32_t base = ent >> 16;
     const bool VEC = (plo & 15u) == 0;
-    uint32_t addr[NX];
     uint32_t st4[4];
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(st4[0]), "=r"(st4[1]), "=r"(st4[2]), "=r"(st4[3]) : "r"(smem_u32(&sw.stride[0])) : "memory");
-    addr[0] = smem_u32(tile) + (ent & 0xFFFFu);
+    // the virtual thread's first amplitude (tile-local index, shared-memory byte offset) comes from the per-pass table
+    // built at kernel start -- it is the same for every tile
+    auto addresses = [&](uint32_t vt, uint32_t (&addr)[NX]) -> uint32_t {
+        const uint32_t ent = tab[vt];
+        addr[0] = smem_u32(tile) + (ent & 0xFFFFu);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st4[j];
-    }
-    float2 a[NX];
-    if (TC_DBG(ctx, 8u)) {
-#pragma unroll
-        for (int x = 0; x < NX; ++x) a[x] = make_float2((float)x, (float)ctx.gtid);
-    } else if (VEC) {
-#pragma unroll
-        for (int x = 0; x < NX; x += 2)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(a[x].x), "=f"(a[x].y), "=f"(a[x + 1].x), "=f"(a[x + 1].y) : "r"(addr[x]) : "memory");
-    } else {
-#pragma unroll
-        for (int x = 0; x < NX; ++x)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[x].x), "=f"(a[x].y) : "r"(addr[x]) : "memory");
-    }
-    if (first_touch) {     // the tile stays ranged (times s, a power of two) until the store-out folds 1 / s back in
-#pragma unroll
-        for (int x = 0; x < NX; ++x) { a[x].x *= ctx.scale; a[x].y *= ctx.scale; }
-    }
-    TC_STAMP(ctx, 2);      // tile in registers (loads issued)
-    if ((flags & 1u) && !TC_DBG(ctx, 128u)) {
-        float2 ph = make_float2(1.0f, 0.0f);
-        if (flags & 2u) run_sweep_ops_dense2(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
-        else run_sweep_ops(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
-        if (flags & 4u) {
-#pragma unroll
-            for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
+            for (int x = 0; x < (1 << j); ++x) addr[x | (1 << j)] = addr[x] + st4[j];
         }
-    }
-    TC_STAMP(ctx, 3);      // register ops done
-    if (tc_slot >= 0) {
-        const uint32_t col = ctx.lane_addr + 16u * h;
-        if (!TC_DBG(ctx, 2u)) {
-            uint32_t hi[NX], lo[NX];       // 8 columns of packed real parts, then 8 of imaginary parts
+        return ent >> 16;
+    };
+    auto store_tile = [&](const float2 (&a)[NX], const uint32_t (&addr)[NX]) {
+        if (TC_DBG(ctx, 8u)) {
+            if (a[3].x == 12345.678f) tile[0] = a[5];       // keep the values alive
+        } else if (VEC) {
 #pragma unroll
-            for (int x = 0; x < NX; x += 2) {
-                split2(a[x].x, a[x + 1].x, hi[x >> 1], lo[x >> 1]);
-                split2(a[x].y, a[x + 1].y, hi[8 + (x >> 1)], lo[8 + (x >> 1)]);
+            for (int x = 0; x < NX; x += 2)
+                asm volatile("st.shared.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(a[x].x), "f"(a[x].y), "f"(a[x + 1].x), "f"(a[x + 1].y),
+                             "r"(addr[x])
+                             : "memory");
+        } else {
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+                asm volatile("st.shared.v2.f32 [%2], {%0, %1};" ::"f"(a[x].x), "f"(a[x].y), "r"(addr[x]) : "memory");
+        }
+    };
+#pragma unroll 1
+    for (int hh = 0; hh < HALVES; ++hh) {
+        const uint32_t vt = (uint32_t)ctx.gtid + (uint32_t)hh * GT, h = vt >> 7;
+        uint32_t addr[NX];
+        const uint32_t base = addresses(vt, addr);
+        float2 a[NX];
+        if (TC_DBG(ctx, 8u)) {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) a[x] = make_float2((float)x, (float)ctx.gtid);
+        } else if (VEC) {
+#pragma unroll
+            for (int x = 0; x < NX; x += 2)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(a[x].x), "=f"(a[x].y), "=f"(a[x + 1].x), "=f"(a[x + 1].y) : "r"(addr[x]) : "memory");
+        } else {
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a[x].x), "=f"(a[x].y) : "r"(addr[x]) : "memory");
+        }
+        if (first_touch) {     // the tile stays ranged (times s, a power of two) until the store-out folds 1 / s back in
+#pragma unroll
+            for (int x = 0; x < NX; ++x) { a[x].x *= ctx.scale; a[x].y *= ctx.scale; }
+        }
+        TC_STAMP(ctx, 2);      // tile in registers (loads issued)
+        if ((flags & 1u) && !TC_DBG(ctx, 128u)) {
+            float2 ph = make_float2(1.0f, 0.0f);
+            if (flags & 2u) run_sweep_ops_dense2(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
+            else run_sweep_ops(a, ph, smem_u32(rops + first), smem_u32(pool), base, outer_ok);
+            if (flags & 4u) {
+#pragma unroll
+                for (int x = 0; x < NX; ++x) a[x] = cmul(ph, a[x]);
             }
-            st16(col + COL_AHI, hi);
-            st16(col + COL_ALO, lo);
         }
-        TC_STAMP(ctx, 4);  // split + tcgen05.st issued
-        wait_st();
-        fence_before();
-        TC_STAMP(ctx, 5);  // stores complete
-        if (!TC_DBG(ctx, 256u)) group_sync(ctx.group);
-        TC_STAMP(ctx, 6);  // barrier passed
-        if ((ctx.gtid >> 5) == 0 && !TC_DBG(ctx, 64u)) {
-            // only this warp watches the completion barrier; the other seven sleep in the group barrier below
-            // (a spinning try_wait loop in every warp took issue slots from the other group's register work)
-            fence_after();
-            if (elect_one()) {
-                if (!TC_DBG(ctx, 1u)) issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)tc_slot * (uint32_t)TC_SLOT_BYTES);
-                commit(ctx.bar);
+        TC_STAMP(ctx, 3);      // register ops done
+        if (tc_slot >= 0) {
+            if (!TC_DBG(ctx, 2u)) {
+                const uint32_t col = ctx.lane_addr + 16u * h;
+                uint32_t hi[NX], lo[NX];       // 8 columns of packed real parts, then 8 of imaginary parts
+#pragma unroll
+                for (int x = 0; x < NX; x += 2) {
+                    split2(a[x].x, a[x + 1].x, hi[x >> 1], lo[x >> 1]);
+                    split2(a[x].y, a[x + 1].y, hi[8 + (x >> 1)], lo[8 + (x >> 1)]);
+                }
+                st16(col + COL_AHI, hi);
+                st16(col + COL_ALO, lo);
             }
-            __syncwarp();
-            TC_STAMP(ctx, 7);  // MMAs issued
-            mbar_wait_bounded(ctx.bar, ctx.phase);
-            TC_STAMP(ctx, 8);  // MMAs complete
+            TC_STAMP(ctx, 4);  // split + tcgen05.st issued
+        } else {
+            store_tile(a, addr);
         }
-        if (!TC_DBG(ctx, 64u)) ctx.phase ^= 1u;
-        if (TC_DBG(ctx, 32u)) { if ((ctx.gtid >> 5) != 0) mbar_wait_bounded(ctx.bar, ctx.phase ^ 1u); }   // every warp watches the barrier itself
-        else if (!TC_DBG(ctx, 256u)) group_sync(ctx.group);
+    }
+    if (tc_slot < 0) return;
+    wait_st();
+    fence_before();
+    TC_STAMP(ctx, 5);  // stores complete
+    if (!TC_DBG(ctx, 256u)) group_sync<GT>(ctx.group);
+    TC_STAMP(ctx, 6);  // barrier passed
+    if ((ctx.gtid >> 5) == 0 && !TC_DBG(ctx, 64u)) {
+        // only this warp watches the completion barrier; the others sleep in the group barrier below
+        // (a spinning try_wait loop in every warp took issue slots from the other groups' register work)
         fence_after();
-        TC_STAMP(ctx, 9);  // second barrier passed
+        if (elect_one()) {
+            if (!TC_DBG(ctx, 1u)) issue_block(ctx.tbase, ctx.bimg0 + (uint32_t)tc_slot * (uint32_t)TC_SLOT_BYTES);
+            commit(ctx.bar);
+        }
+        __syncwarp();
+        TC_STAMP(ctx, 7);  // MMAs issued
+        mbar_wait_bounded(ctx.bar, ctx.phase);
+        TC_STAMP(ctx, 8);  // MMAs complete
+    }
+    if (!TC_DBG(ctx, 64u)) ctx.phase ^= 1u;
+    if (TC_DBG(ctx, 32u)) { if ((ctx.gtid >> 5) != 0) mbar_wait_bounded(ctx.bar, ctx.phase ^ 1u); }   // every warp watches the barrier itself
+    else if (!TC_DBG(ctx, 256u)) group_sync<GT>(ctx.group);
+    fence_after();
+    TC_STAMP(ctx, 9);  // second barrier passed
+#pragma unroll 1
+    for (int hh = 0; hh < HALVES; ++hh) {
+        const uint32_t vt = (uint32_t)ctx.gtid + (uint32_t)hh * GT, h = vt >> 7;
+        const uint32_t col = ctx.lane_addr + 16u * h;
+        uint32_t addr[NX];
+        (void)addresses(vt, addr);
+        float2 a[NX];
         if (!TC_DBG(ctx, 4u)) {
             uint32_t re[NX], im[NX];
             ld16(col + COL_D, re);
@@ -257,75 +291,71 @@ __device__ __forceinline__ void sweep(float2 *tile, const Sweep &sw, const uint3
             wait_ld();
 #pragma unroll
             for (int x = 0; x < NX; ++x) { a[x].x = __uint_as_float(re[x]); a[x].y = __uint_as_float(im[x]); }
+        } else {
+#pragma unroll
+            for (int x = 0; x < NX; ++x) a[x] = make_float2((float)x, (float)ctx.gtid);
         }
-        fence_before();        // orders these tensor-memory reads before the next sweep's barrier + MMA
         TC_STAMP(ctx, 10); // D in registers
+        store_tile(a, addr);
     }
-    if (TC_DBG(ctx, 8u)) {
-        if (a[3].x == 12345.678f) tile[0] = a[5];       // keep the values alive
-    } else if (VEC) {
-#pragma unroll
-        for (int x = 0; x < NX; x += 2)
-            asm volatile("st.shared.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(a[x].x), "f"(a[x].y), "f"(a[x + 1].x), "f"(a[x + 1].y),
-                         "r"(addr[x])
-                         : "memory");
-    } else {
-#pragma unroll
-        for (int x = 0; x < NX; ++x)
-            asm volatile("st.shared.v2.f32 [%2], {%0, %1};" ::"f"(a[x].x), "f"(a[x].y), "r"(addr[x]) : "memory");
-    }
+    fence_before();        // orders these tensor-memory reads before the next sweep's barrier + MMA
     TC_STAMP(ctx, 11);     // tile stores issued
 }
 
 }  // namespace tc
 
-// Persistent CTAs of two 256-thread groups; group g of CTA b is "virtual CTA" 2b + g of the tile loop of
-// tile_kernel_pipe (same staging, same store epilogue), with a 2-stage cp.async ring of its own.
-template <typename Prog>
-__global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const __grid_constant__ Prog P) {
+// Persistent CTAs of 512 threads in NG = 512 / GT groups that stream different tiles (group g of CTA b is "virtual CTA"
+// NG b + g of the tile loop of tile_kernel_pipe: same cp.async staging, same store epilogue), so that one group's
+// shared-memory and split work overlaps the others' MMAs.  GT = 256: two groups, a 2-stage ring each (the next tile is
+// prefetched).  GT = 128: four groups with ONE stage each -- a group waits for its own tile, the other three keep the
+// SM busy -- and every thread owns a whole row of the tile (two halves of 16 amplitudes, one after the other).
+template <typename Prog, int GT>
+__global__ void __launch_bounds__(512, 1) tile_kernel_tc(const __grid_constant__ Prog P) {
     using C = float2;
     using Layout = PaddedLayout<C>;
-    constexpr int MT = TILE_MIN_BITS_C64, NT = TC_GROUP_THREADS, VSHIFT = 1, NK = 8, S = TC_STAGES;
+    constexpr int MT = TILE_MIN_BITS_C64, NT = GT, NG = 512 / GT, HALVES = 256 / GT, VSHIFT = 1;
+    constexpr int NKB = GT == 256 ? 3 : 4, NK = 1 << NKB;       // vectors per thread of a tile's staging and store-out
+    constexpr int S = GT == 256 ? 2 : 1;
+    constexpr uint32_t TCOLS = 512 / NG;
     extern __shared__ __align__(128) unsigned char smem_all[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t mma_bar[2];
-    const int tid = threadIdx.x, g = tid >> 8, gtid = tid & (NT - 1);
+    __shared__ __align__(8) uint64_t mma_bar[4];
+    const int tid = threadIdx.x, g = tid / GT, gtid = tid % GT;
     ProgView pv;
     const uint64_t *chunk_off;
-    const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, 2 * NT);
-    // flat offsets of the top three tile bits, in registers (in vector units): vector k of a thread sits at the OR of those
-    // whose bit of k is set -- no table look-ups in the load and store loops
-    uint64_t top_off[3];
-    for (int j = 0; j < 3; ++j) {
-        const int i = TILE_MIN_BITS_C64 - 3 + j;
-        top_off[j] = (1ull << (i < P.L ? i : P.hbits[i - P.L])) * sizeof(float2);      // in bytes
+    const uint32_t prog_bytes = stage_program(smem_all, P, pv, chunk_off, tid, 512);
+    // flat offsets (in bytes) of the top tile bits, in registers: vector k of a thread sits at the sum of those whose
+    // bit of k is set -- no table look-ups in the load and store loops
+    uint64_t top_off[NKB];
+    for (int j = 0; j < NKB; ++j) {
+        const int i = TILE_MIN_BITS_C64 - NKB + j;
+        top_off[j] = (1ull << (i < P.L ? i : P.hbits[i - P.L])) * sizeof(float2);
     }
     (void)chunk_off;
-    // per-sweep, per-thread addressing table: (tile-local index of the thread's first amplitude) << 16 | its byte offset in
-    // a stage.  Thread (rho, h) of a group owns row rho; h is inserted at rank `hrank` among the 8 thread bits and a zero
-    // at each of the four register-bit positions.
+    // per-sweep addressing table of the 256 virtual threads: (tile-local index of the first amplitude) << 16 | its byte
+    // offset in a stage.  Virtual thread (rho, h) owns half h of row rho; h is inserted at rank `hrank` among the 8
+    // thread bits and a zero at each of the four register-bit positions.
     uint32_t *swtab = reinterpret_cast<uint32_t *>(smem_all + prog_bytes);
-    for (uint32_t i = tid; i < (uint32_t)P.nsweeps * NT; i += 2 * NT) {
-        const Sweep &sw = P.sweeps[i / NT];
+    for (uint32_t i = tid; i < (uint32_t)P.nsweeps * 256u; i += 512u) {
+        const Sweep &sw = P.sweeps[i >> 8];
         if (sw.kind != SWEEP_REG) continue;
-        const uint32_t t = i % NT, rho = t & 127u, hh = t >> 7, p = (uint32_t)sw.hrank;
+        const uint32_t t = i & 255u, rho = t & 127u, hh = t >> 7, p = (uint32_t)sw.hrank;
         uint32_t base = ((rho >> p) << (p + 1)) | (hh << p) | (rho & ((1u << p) - 1u));
         for (int j = 0; j < 4; ++j) base += base & (0xFFFFFFFFu << sw.rpos[j]);
         swtab[i] = (base << 16) | (Layout::amp(base) * (uint32_t)sizeof(float2));
     }
     // block-matrix images
-    unsigned char *bimg = smem_all + prog_bytes + (size_t)P.nsweeps * NT * sizeof(uint32_t);
+    unsigned char *bimg = smem_all + prog_bytes + (size_t)P.nsweeps * 256u * sizeof(uint32_t);
     {
         const uint4 *srcm = reinterpret_cast<const uint4 *>(P.tc_mats);
         uint4 *dstm = reinterpret_cast<uint4 *>(bimg);
         const uint32_t nvec = (uint32_t)P.n_tc * (TC_SLOT_BYTES / 16);
-        for (uint32_t i = tid; i < nvec; i += 2 * NT) dstm[i] = srcm[i];
+        for (uint32_t i = tid; i < nvec; i += 512u) dstm[i] = srcm[i];
     }
     unsigned char *ring = bimg + (size_t)P.n_tc * TC_SLOT_BYTES + (size_t)g * S * Layout::bytes(MT);
     if (tid < 32) tc::tmem_alloc(&tmem_slot, 512);
     if (tid == 32) {
-        mbar_init(&mma_bar[0], 1);
-        mbar_init(&mma_bar[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&mma_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the images were written through the generic proxy
@@ -334,7 +364,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     tc::fence_after();
     tc::Ctx ctx;
     ctx.group = g; ctx.gtid = gtid; ctx.phase = 0; ctx.bar = &mma_bar[g];
-    ctx.tbase = tmem_slot + 256u * (uint32_t)g;
+    ctx.tbase = tmem_slot + TCOLS * (uint32_t)g;
     ctx.lane_addr = ctx.tbase + ((uint32_t)(((gtid >> 5) & 3) * 32) << 16);
     ctx.bimg0 = smem_u32(bimg);
     {
@@ -362,7 +392,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         fr = (float)(s * P.gphase[0]); fi = (float)(s * P.gphase[1]);
     }
     uint64_t low_tid = 0;
-    for (int b = 0; b < MT - 3 - VSHIFT; ++b)
+    for (int b = 0; b < MT - NKB - VSHIFT; ++b)
         if ((gtid >> b) & 1) {
             const int i = b + VSHIFT;
             low_tid |= 1ull << (i < L ? i : P.hbits[i - L]);
@@ -370,7 +400,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
     const uint4 *src = reinterpret_cast<const uint4 *>(P.src) + (low_tid >> VSHIFT);
     uint4 *dst = reinterpret_cast<uint4 *>(P.dst) + (low_tid >> VSHIFT);
     double nacc[1] = {0.0};
-    const uint64_t vcta = 2ull * blockIdx.x + (uint64_t)g, vgrid = 2ull * gridDim.x;
+    const uint64_t vcta = (uint64_t)NG * blockIdx.x + (uint64_t)g, vgrid = (uint64_t)NG * gridDim.x;
     const uint64_t my_tiles = (P.ntiles > vcta) ? (P.ntiles - 1 - vcta) / vgrid + 1 : 0;
     const float2 *pool = reinterpret_cast<const float2 *>(pv.pool);
 
@@ -379,11 +409,11 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         const uint64_t base = tile_base_of(vcta + it * vgrid, P);
         next_base = base;
         const uint32_t sp = smem_u32(ring + (size_t)st * stage_bytes) + svec_tid * 16u;
-        // the 8 vectors of a thread: one pointer + the three top-bit offsets (7 additions, no per-vector index arithmetic)
+        // the vectors of a thread: one pointer + the top-bit offsets (NK - 1 additions, no per-vector index arithmetic)
         const unsigned char *gptr[NK];
         gptr[0] = reinterpret_cast<const unsigned char *>(src) + base * sizeof(float2);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < NKB; ++j) {
 #pragma unroll
             for (int k = 0; k < (1 << j); ++k) gptr[k | (1 << j)] = gptr[k] + top_off[j];
         }
@@ -405,12 +435,14 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         eval_outer(pv, base, parity, gtid);
         cp_async_wait_pending(0);          // this thread's copies of tile `it` have landed
         TC_STAMP(ctx, 21);
-        tc::group_sync(g);                 // ... everyone's have, and the other stage is drained
+        tc::group_sync<GT>(g);             // ... everyone's have, and the other stage is drained
         TC_STAMP(ctx, 22);
         // (issuing the next tile's copies later -- while the tensor core works on this tile's first block -- was measured
         // slower: 202 vs 182 ms on the headline circuit)
-        if (it + 1 < my_tiles) issue_load(it + 1, st ^ 1);
-        cp_async_commit();
+        if (S > 1) {
+            if (it + 1 < my_tiles) issue_load(it + 1, st ^ 1);
+            cp_async_commit();
+        }
         unsigned char *stage = ring + (size_t)st * stage_bytes;
         const uint64_t outer_ok = (pv.nouter ? pv.outer_ok[parity] : 0ull) | (1ull << OUTER_SLOT_NONE);
         bool ranged = false;
@@ -418,11 +450,11 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
             if (TC_DBG(ctx, 512u)) break;                          // (timing experiment: staging and store-out only)
             const Sweep &sw = pv.sweeps[s];
             if (sw.kind == SWEEP_REG) {
-                tc::sweep<Layout>(reinterpret_cast<C *>(stage), sw, swtab + s * NT, pv.regops, pool, outer_ok, ctx, !ranged);
+                tc::sweep<Layout, HALVES>(reinterpret_cast<C *>(stage), sw, swtab + s * 256, pv.regops, pool, outer_ok, ctx, !ranged);
                 ranged = true;
             }
             else apply_generic<float, Layout>(reinterpret_cast<C *>(stage), MT, pv.gen[sw.first], pool, base, gtid, NT);
-            tc::group_sync(g);
+            tc::group_sync<GT>(g);
             TC_STAMP(ctx, 12);     // end-of-sweep barrier passed
         }
         TC_STAMP(ctx, 23);
@@ -431,7 +463,7 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
         unsigned char *optr[NK];
         optr[0] = reinterpret_cast<unsigned char *>(dst) + base * sizeof(float2);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < NKB; ++j) {
 #pragma unroll
             for (int k = 0; k < (1 << j); ++k) optr[k | (1 << j)] = optr[k] + top_off[j];
         }
@@ -444,7 +476,13 @@ __global__ void __launch_bounds__(2 * TC_GROUP_THREADS, 1) tile_kernel_tc(const 
             *reinterpret_cast<uint4 *>(optr[k]) = val;
         }
         nacc[0] += (double)tacc;
-        st ^= 1;
+        if (S > 1) st ^= 1;
+        else {
+            // one stage: the next tile is copied over this one as soon as it has been read out (a thread's copies land in
+            // the slots the same thread has just read)
+            if (it + 1 < my_tiles) issue_load(it + 1, 0);
+            cp_async_commit();
+        }
         TC_STAMP(ctx, 24);         // store-out issued
     }
     cp_async_wait_pending(0);

@@ -288,7 +288,7 @@ template <typename Prog>
 static uint32_t program_smem_bytes(const Prog &P) {
     return align128(align16(P.nsweeps * (uint32_t)sizeof(Sweep)) + align16(P.nregops * (uint32_t)sizeof(RegOp)) +
                     align16(P.nouter * (uint32_t)sizeof(OuterPred)) + align16(P.ngen * (uint32_t)sizeof(TileOp)) +
-                    align16((uint32_t)P.mat_bytes) + 32u + (uint32_t)sizeof(uint64_t) * ((1u << P.H) + 8u));
+                    align16((uint32_t)P.mat_bytes) + 64u + (uint32_t)sizeof(uint64_t) * ((1u << P.H) + 8u));
 }
 
 __device__ __forceinline__ void copy_words(void *dst, const void *src, uint32_t bytes, int tid, int nt) {
@@ -317,8 +317,8 @@ __device__ __forceinline__ uint32_t stage_program(unsigned char *smem, const Pro
     pv.pool = smem + o;
     copy_words(smem + o, P.mats, (uint32_t)P.mat_bytes, tid, nt);
     o += align16((uint32_t)P.mat_bytes);
-    pv.outer_ok = reinterpret_cast<uint64_t *>(smem + o);      // [2 tile parities] x [2 groups of the tensor-core kernel]
-    o += 32u;
+    pv.outer_ok = reinterpret_cast<uint64_t *>(smem + o);      // [2 tile parities] x [up to 4 groups of the tensor-core kernel]
+    o += 64u;
     uint64_t *co = reinterpret_cast<uint64_t *>(smem + o);
     for (uint32_t c = tid; c < (1u << P.H); c += nt) {
         uint64_t off = 0;
@@ -933,10 +933,11 @@ static int tc_upload(const unsigned char *images, int nslots, void *ws, cudaStre
     return QCS_OK;
 }
 
-template <typename Prog>
-static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
+template <typename Prog, int GT>
+static int launch_tc_groups(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
     using Layout = PaddedLayout<float2>;
-    auto kern = tile_kernel_tc<Prog>;
+    auto kern = tile_kernel_tc<Prog, GT>;
+    constexpr int NG = 512 / GT, STAGES = GT == 256 ? 2 : 1;
     static bool attr_done[64] = {};
     int device = 0;
     cudaGetDevice(&device);
@@ -946,13 +947,13 @@ static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
             return set_error(QCS_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
         if (device < 64) attr_done[device] = true;
     }
-    const size_t smem = program_smem_bytes(P) + (size_t)P.nsweeps * TC_GROUP_THREADS * sizeof(uint32_t) + (size_t)P.n_tc * TC_SLOT_BYTES +
-                        2 * TC_STAGES * Layout::bytes(TILE_MIN_BITS_C64);
+    const size_t smem = program_smem_bytes(P) + (size_t)P.nsweeps * 256 * sizeof(uint32_t) + (size_t)P.n_tc * TC_SLOT_BYTES +
+                        (size_t)NG * STAGES * Layout::bytes(TILE_MIN_BITS_C64);
     if (smem > (size_t)SMEM_LIMIT) return set_error(QCS_ERR_UNSUPPORTED, "tensor-core pass does not fit shared memory");
-    P.stages = TC_STAGES;
+    P.stages = STAGES;
     uint64_t grid = (uint64_t)dev.sms;
-    if (grid * 2 > P.ntiles) grid = (P.ntiles + 1) / 2;
-    kern<<<(unsigned)grid, 2 * TC_GROUP_THREADS, smem, stream>>>(P);
+    if (grid * NG > P.ntiles) grid = (P.ntiles + NG - 1) / NG;
+    kern<<<(unsigned)grid, 512, smem, stream>>>(P);
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) {
         static thread_local char msg[160];
@@ -961,6 +962,13 @@ static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
         return set_error(QCS_ERR_CUDA, msg);
     }
     return QCS_OK;
+}
+
+template <typename Prog>
+static int launch_tc(Prog &P, const DeviceInfo &dev, cudaStream_t stream) {
+    // four groups of 128 threads (one stage each) or two of 256 (two stages each): QCS_TC_GROUPS
+    if (tune_int("QCS_TC_GROUPS", TC_DEFAULT_GROUPS) == 4) return launch_tc_groups<Prog, 128>(P, dev, stream);
+    return launch_tc_groups<Prog, 256>(P, dev, stream);
 }
 
 template <typename Prog>
