@@ -184,6 +184,29 @@ def test_ranging_of_the_fp16_operands():
         assert err < TOL, name
 
 
+def test_both_group_layouts_of_the_kernel(monkeypatch):
+    """four groups of 128 threads (default: a thread owns a whole row, two halves) and two groups of 256 (a 2-stage
+    ring each) run the same plan: both against the oracle, and bit-identical to each other"""
+    rng = np.random.default_rng(21)
+    n = 17
+    vec = rand_state_vec(rng, n)
+    gates = []
+    for block in ([0, 1, 2, 3, 4], [5, 6, 7, 8, 9], [2, 4, 6, 8, 10], [7, 8, 9, 10, 11]):
+        for _ in range(6):
+            a, b = (int(v) for v in rng.choice(block, size=2, replace=False))
+            gates.append((rand_unitary(rng, 2), [a, b]))
+        gates.append((_ctrl(_rx(0.4)), [14, block[1]]))          # a control outside the tile: register op
+        gates.append((_rz(0.9), [16]))
+    results = {}
+    for groups in ('4', '2'):
+        monkeypatch.setenv('QCS_TC_GROUPS', groups)
+        got, want, st = _run(n, vec, gates)
+        assert st[7] & 255 >= 3
+        assert rel_err(got, want) < TOL
+        results[groups] = got
+    assert np.array_equal(results['4'], results['2'])
+
+
 def test_layered_circuit_through_the_scheduler():
     """Circuit.run on the headline workload's generator at 20 qubits (depth 40, 1 180 gates) vs the oracle"""
     from qcircuits_b200.workloads import layered_circuit, layered_gate_list, operator_for
