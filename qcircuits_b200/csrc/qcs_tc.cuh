@@ -333,15 +333,35 @@ __global__ void __launch_bounds__(512, 1) tile_kernel_tc(const __grid_constant__
     }
     (void)chunk_off;
     // per-sweep addressing table of the 256 virtual threads: (tile-local index of the first amplitude) << 16 | its byte
-    // offset in a stage.  Virtual thread (rho, h) owns half h of row rho; h is inserted at rank `hrank` among the 8
-    // thread bits and a zero at each of the four register-bit positions.
+    // offset in a stage.  Virtual thread (rho, h) owns half h of row rho: h is the block's thread bit (rank `hrank` among
+    // the 8 non-register tile bits), the 7 bits of rho are the other non-register bits -- in an order chosen so that
+    // the lanes of one shared-memory wavefront (16 lanes of 8-byte accesses, or 8 lanes of 16-byte accesses when tile bit
+    // 0 is a register bit) fall on different banks: in the padded layout tile bit b moves an amplitude by 8 bytes (b =
+    // 0) or 16 / 32 / 64 bytes mod 128 (b = 1, 2, 3 mod 3), so the low lane bits take one tile bit of each class.  Rows
+    // are independent in the MMA and the register ops see the index through `base`, so any order is legal.
     uint32_t *swtab = reinterpret_cast<uint32_t *>(smem_all + prog_bytes);
     for (uint32_t i = tid; i < (uint32_t)P.nsweeps * 256u; i += 512u) {
         const Sweep &sw = P.sweeps[i >> 8];
         if (sw.kind != SWEEP_REG) continue;
-        const uint32_t t = i & 255u, rho = t & 127u, hh = t >> 7, p = (uint32_t)sw.hrank;
-        uint32_t base = ((rho >> p) << (p + 1)) | (hh << p) | (rho & ((1u << p) - 1u));
-        for (int j = 0; j < 4; ++j) base += base & (0xFFFFFFFFu << sw.rpos[j]);
+        uint32_t regmask = 0;
+        for (int j = 0; j < 4; ++j) regmask |= 1u << sw.rpos[j];
+        int tb[8], nt = 0;                             // the non-register tile bits, ascending
+        for (int b = 0; b < MT; ++b)
+            if (!((regmask >> b) & 1u)) tb[nt++] = b;
+        const int hbit = tb[sw.hrank];
+        int order[7], no = 0;
+        uint32_t used = 1u << hbit;
+        if (!(regmask & 1u) && hbit != 0) { order[no++] = 0; used |= 1u; }          // 8-byte accesses: bit 0 first
+        for (int cls = 0; cls < 3; ++cls)                                             // then one bit of each class
+            for (int k = 0; k < 8; ++k) {
+                const int b = tb[k];
+                if (b >= 1 && !((used >> b) & 1u) && (b - 1) % 3 == cls) { order[no++] = b; used |= 1u << b; break; }
+            }
+        for (int k = 0; k < 8; ++k)                                                   // the rest, ascending
+            if (!((used >> tb[k]) & 1u)) { order[no++] = tb[k]; used |= 1u << tb[k]; }
+        const uint32_t t = i & 255u, rho = t & 127u, hh = t >> 7;
+        uint32_t base = hh << hbit;
+        for (int j = 0; j < 7; ++j) base |= ((rho >> j) & 1u) << order[j];
         swtab[i] = (base << 16) | (Layout::amp(base) * (uint32_t)sizeof(float2));
     }
     // block-matrix images

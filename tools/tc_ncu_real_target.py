@@ -21,15 +21,17 @@ def main():
     s = qc.zeros(n, dtype=np.complex64)
     s = qc.Hadamard()(s, qubit_indices=[0])
     buf = s._dv.buf.data_ptr()
+    unit = torch.ones(2, dtype=torch.float64, device='cuda')     # the state is normalised: its lazy squared norm (ranges the fp16 operands)
+    norm_in = unit.data_ptr()
     ws, stream = _lib.workspace().data_ptr(), _lib.stream_ptr()
     stats = (ctypes.c_int32 * 128)()
     for idx in (2, 8):                      # passes with four blocks and few register ops (L = 4 / 5 tiles)
         item = comp[idx]
         _lib.check(lib.qcs_plan_stats(n, 0, item[1], len(item[1]), stats))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        _lib.check(lib.qcs_apply_fused(buf, buf, n, 0, item[1], len(item[1]), None, None, ws, stream))
+        _lib.check(lib.qcs_apply_fused(buf, buf, n, 0, item[1], len(item[1]), norm_in, None, ws, stream))
         e0.record()
-        _lib.check(lib.qcs_apply_fused(buf, buf, n, 0, item[1], len(item[1]), None, None, ws, stream))
+        _lib.check(lib.qcs_apply_fused(buf, buf, n, 0, item[1], len(item[1]), norm_in, None, ws, stream))
         e1.record()
         torch.cuda.synchronize()
         print('pass %d: %d gates, %d sweeps (%d with a block, %d gates in blocks), %d register ops: %.3f ms' % (
