@@ -181,8 +181,11 @@ class State(Tensor):
         return amp
 
     def schmidt_number(self, indices):
-        """Schmidt number across the cut (indices | rest) (state.py:225-260).  Host SVD of the
-        exported tensor: LAPACK work on a reshaped copy, outside the device hot path."""
+        """Schmidt number across the cut (indices | rest) (state.py:225-260).  The reference transposes the tensor so
+        that the listed qubits come first, reshapes it into a 2^a x 2^b matrix and counts its singular values above
+        1e-10.  Here the relabelling is the device bit permutation (qcs_permute_bits), the matrix is a view of the
+        permuted buffer and the singular values come from the device solver (torch.linalg.svdvals in float64, the
+        reference's precision): nothing of the state goes through the host."""
         if len(indices) in [0, self.rank]:
             raise ValueError('At least one qubit index should be included '
                              'and at least one should be excluded')
@@ -192,8 +195,17 @@ class State(Tensor):
             raise ValueError('Indices should be integers.')
         inside = set(indices)
         outside = set(range(self.rank)) - inside
-        M = self._t.transpose(list(inside) + list(outside)).reshape(2 ** len(inside), 2 ** len(outside))
-        return np.sum(np.linalg.svd(M, compute_uv=False) > 1e-10)
+        d = self.rank
+        axes = list(inside) + list(outside)
+        src_bit = [0] * d
+        for new_q, old_q in enumerate(axes):
+            src_bit[d - 1 - new_q] = d - 1 - old_q
+        dv = self._dv.permuted(src_bit)
+        t = _lib.torch()
+        M = t.view_as_complex(dv.buf.view(-1, 2)).reshape(2 ** len(inside), 2 ** len(outside)).to(t.complex128)
+        if dv.norm is not None:
+            M = M / t.sqrt(dv.norm[0])
+        return int((t.linalg.svdvals(M) > 1e-10).sum().item())
 
     # -- application of an operator (called by Operator._apply) -------------------------------------------
     def _apply_operator(self, op, qubit_indices):

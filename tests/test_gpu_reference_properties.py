@@ -128,6 +128,25 @@ def test_kronecker_convention_against_dense_matrix():
     assert np.allclose((qc.PauliX() * qc.Identity()).to_matrix(), np.kron([[0, 1], [1, 0]], np.eye(2)))
 
 
+def test_schmidt_number_on_the_device_matches_a_host_svd():
+    """state.py:225-260 -- random states built as sums of r product terms across a cut have Schmidt number r"""
+    rng = np.random.default_rng(3)
+    for d, cut, r in ((6, [0, 1, 2], 3), (7, [1, 4], 2), (8, [0, 2, 5, 7], 5), (5, [4], 1), (9, [3, 8, 0], 8)):
+        a, b = len(cut), d - len(cut)
+        rest = [q for q in range(d) if q not in cut]
+        M = np.zeros((2 ** a, 2 ** b), dtype=np.complex128)
+        for _ in range(r):
+            M += np.outer(rng.normal(size=2 ** a) + 1j * rng.normal(size=2 ** a),
+                          rng.normal(size=2 ** b) + 1j * rng.normal(size=2 ** b))
+        M /= np.linalg.norm(M)
+        # tensor with the cut qubits first, then moved to their places
+        tens = np.moveaxis(M.reshape([2] * d), list(range(d)), cut + rest)
+        s = qc.State(tens)
+        want = int(np.sum(np.linalg.svd(M, compute_uv=False) > 1e-10))
+        assert want == min(r, 2 ** a, 2 ** b)
+        assert s.schmidt_number(cut) == want
+
+
 def test_schmidt_number_and_arithmetic():
     """SchmidtTests / addition and scalar multiplication tests (tests.py:652-705, 875-924)."""
     assert qc.bell_state(0, 0).schmidt_number([0]) == 2
