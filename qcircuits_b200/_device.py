@@ -19,10 +19,13 @@ def _ptr(t):
 
 
 class DeviceVector:
-    __slots__ = ('buf', 'norm', 'nbits', 'dtype')
+    __slots__ = ('buf', 'norm', 'nbits', 'dtype', 'bound')
 
-    def __init__(self, buf, norm, nbits, dtype):
+    def __init__(self, buf, norm, nbits, dtype, bound=None):
         self.buf, self.norm, self.nbits, self.dtype = buf, norm, nbits, np.dtype(dtype)
+        # device scalar >= the squared norm of ``buf`` when that is known without measuring (a basis state: 1), else
+        # None.  It only ranges the fp16 operands of the tensor-core sweeps (qcs_apply_fused_bounded) when ``norm`` is None.
+        self.bound = bound
 
     # -- construction / export ---------------------------------------------------------------------
     @classmethod
@@ -37,7 +40,7 @@ class DeviceVector:
     def basis(cls, nbits, index, dtype):
         buf = _lib.alloc_amplitudes(nbits, dtype)
         check(_lib.load().qcs_set_basis(buf.data_ptr(), nbits, _lib.dtype_code(dtype), index, _lib.stream_ptr()))
-        return cls(buf, None, nbits, dtype)
+        return cls(buf, None, nbits, dtype, bound=_lib.unit_scalar())
 
     @property
     def code(self):
@@ -51,7 +54,8 @@ class DeviceVector:
         return v
 
     def clone(self):
-        return DeviceVector(self.buf.clone(), None if self.norm is None else self.norm.clone(), self.nbits, self.dtype)
+        return DeviceVector(self.buf.clone(), None if self.norm is None else self.norm.clone(), self.nbits, self.dtype,
+                            bound=self.bound)
 
     def _new_like(self, nbits=None):
         nbits = self.nbits if nbits is None else nbits
@@ -65,8 +69,9 @@ class DeviceVector:
         dst = self._new_like() if out is None else out
         norm_out = _lib.alloc_scalar() if track_norm else None
         ws = _lib.workspace()
-        check(lib.qcs_apply_fused(dst.buf.data_ptr(), self.buf.data_ptr(), self.nbits, self.code, ops, len(ops),
-                                  _ptr(self.norm), _ptr(norm_out), ws.data_ptr(), _lib.stream_ptr()))
+        bound = self.bound if self.norm is None else None
+        check(lib.qcs_apply_fused_bounded(dst.buf.data_ptr(), self.buf.data_ptr(), self.nbits, self.code, ops, len(ops),
+                                          _ptr(self.norm), _ptr(norm_out), _ptr(bound), ws.data_ptr(), _lib.stream_ptr()))
         dst.norm = norm_out
         del keep
         return dst

@@ -172,6 +172,19 @@ def alloc_scalar():
     return t.empty(2, dtype=t.float64, device='cuda')
 
 
+_units = {}
+
+
+def unit_scalar():
+    """device float64 holding 1.0 (per device, never written): the squared norm of a basis state"""
+    t = require_cuda()
+    dev = t.cuda.current_device()
+    u = _units.get(dev)
+    if u is None:
+        u = _units[dev] = t.ones(2, dtype=t.float64, device='cuda')
+    return u
+
+
 def upload(array, np_dtype):
     """Host complex array (any shape) -> flat device buffer of interleaved reals."""
     t = require_cuda()

@@ -374,12 +374,14 @@ class Circuit:
         cur = DeviceVector(_lib.alloc_amplitudes(src.nbits, src.dtype), None, src.nbits, src.dtype)
         norms = [_lib.alloc_scalar(), _lib.alloc_scalar()]
         norm_in = None if src.norm is None else src.norm.data_ptr()
+        # a state whose norm is known without measuring (a basis state) ranges the first pass's tensor-core operands
+        bound = src.bound.data_ptr() if (src.norm is None and src.bound is not None) else None
         src_ptr, which = src.buf.data_ptr(), 0
         for item in self._compiled(src.dtype, fuse, max_ops):
             norm_out = norms[which].data_ptr()
             if item[0] == 'tile':
-                _lib.check(lib.qcs_apply_fused(cur.buf.data_ptr(), src_ptr, self.n, code, item[1], len(item[1]),
-                                               norm_in, norm_out, ws, stream))
+                _lib.check(lib.qcs_apply_fused_bounded(cur.buf.data_ptr(), src_ptr, self.n, code, item[1], len(item[1]),
+                                                       norm_in, norm_out, bound, ws, stream))
             else:
                 g = item[1]
                 if src_ptr == cur.buf.data_ptr():      # the dense path is out of place
@@ -388,7 +390,7 @@ class Circuit:
                 _lib.check(lib.qcs_apply_dense(cur.buf.data_ptr(), src_ptr, self.n, code,
                                                g.op._device_matrix(src.dtype).data_ptr(), g.plan.k,
                                                _lib.int32_array(g.bits), norm_in, norm_out, ws, stream))
-            src_ptr, norm_in = cur.buf.data_ptr(), norm_out
+            src_ptr, norm_in, bound = cur.buf.data_ptr(), norm_out, None
             cur.norm = norms[which]
             which ^= 1
         return State(cur)
