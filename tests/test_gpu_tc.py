@@ -184,6 +184,39 @@ def test_ranging_of_the_fp16_operands():
         assert err < TOL, name
 
 
+def test_bounded_entry_point_ranges_with_the_callers_bound():
+    """qcs_apply_fused_bounded (include/qcs.h): a caller that keeps no lazy norm hands over a bound of the squared norm --
+    the sharded engine passes the norm of the WHOLE state to every shard.  Exact, loose (x 64) and per-shard-small cases
+    (a shard that holds 2^-12 of the norm) stay within the tolerance relative to the largest amplitude of the state."""
+    rng = np.random.default_rng(13)
+    n = 16
+    gates = []
+    for _ in range(30):
+        a, b = (int(v) for v in rng.choice(6, size=2, replace=False))
+        gates.append((rand_unitary(rng, 2), [2 + a, 2 + b]))
+    lib = _lib.load()
+    ops, keep = make_ops([(_gates.analyze(M), bits, False) for M, bits in gates])
+    stats = (ctypes.c_int32 * 128)()
+    _lib.check(lib.qcs_plan_stats(n, _lib.QCS_C64, ops, len(ops), stats))
+    assert stats[7] & 255 >= 1
+    t = _lib.torch()
+    vec = rand_state_vec(rng, n)
+    for name, scale, bound2 in (('exact bound', 1.0, 1.0), ('loose bound', 1.0, 64.0), ('small shard', 2.0 ** -6, 1.0)):
+        v = vec * scale
+        want = v.copy()
+        for M, bits in gates:
+            want = orc.apply_matrix_flat(M, want, bits, renorm=False)
+        buf = t.from_numpy(v.astype(np.complex64).view(np.float32)).cuda()
+        bound = t.tensor([bound2, 0.0], dtype=t.float64, device='cuda')
+        _lib.check(lib.qcs_apply_fused_bounded(buf.data_ptr(), buf.data_ptr(), n, _lib.QCS_C64, ops, len(ops), None, None,
+                                               bound.data_ptr(), _lib.workspace().data_ptr(), _lib.stream_ptr()))
+        got = buf.cpu().numpy().view(np.complex64).astype(np.complex128)
+        # the bar of the sharded state: relative to the largest amplitude of the WHOLE state (norm 1 over 2^16 amplitudes)
+        err = np.max(np.abs(got - want)) / np.max(np.abs(vec))
+        print('%s: error / tolerance %.4f' % (name, err / TOL))
+        assert err < TOL, name
+
+
 def test_both_group_layouts_of_the_kernel(monkeypatch):
     """four groups of 128 threads (default: a thread owns a whole row, two halves) and two groups of 256 (a 2-stage
     ring each) run the same plan: both against the oracle, and equal to each other up to the order in which the
