@@ -351,22 +351,23 @@ def main():
         del rho
         torch.cuda.empty_cache()
 
-    # how the passes run, and what the tensor-core blocks amount to: a block applies 36 tcgen05.mma per 128-row tile
-    # (12 x M128 N64 K8 + 24 x M128 N32 K8, the 3-term TF32 split) = 3.15 MFLOP per tile of 2^12 amplitudes
+    # how the passes run, and what the tensor-core blocks amount to: a block applies 18 tcgen05.mma kind::f16 per 128-row
+    # tile (6 x M128 N64 K16 + 12 x M128 N32 K16: hi.hi + hi.lo + lo.hi of the two-term fp16 split) = 3.15 MFLOP per
+    # tile of 2^12 amplitudes
     plan = circ.plan_summary(np_dtype, fuse=fuse, max_ops=args.max_ops)
     tensor = None
     if plan['blocks']:
-        flop = plan['blocks'] * (2.0 ** n / 4096.0) * (12 * 128 * 64 * 8 * 2 + 24 * 128 * 32 * 8 * 2)
+        flop = plan['blocks'] * (2.0 ** n / 4096.0) * (6 * 128 * 64 * 16 * 2 + 12 * 128 * 32 * 16 * 2)
         try:
             with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-                tf32_peak = float(json.load(f)['bf16_tflops_sustained']) / 2.0
-            tf32_src = 'MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)'
+                f16_peak = float(json.load(f)['bf16_tflops_sustained'])
+            f16_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (fp16 runs at the bf16 rate)'
         except Exception:
-            tf32_peak, tf32_src = 700.0, 'B200_PROFILING.md fallback 1.4 PFLOP/s sustained bf16 / 2'
-        tensor = {'tf32_tflops_achieved_over_the_step': flop / (ms_per_step * 1e-3) / 1e12, 'tf32_peak_tflops': tf32_peak,
-                  'frac': flop / (ms_per_step * 1e-3) / 1e12 / tf32_peak, 'peak_source': tf32_src,
-                  'note': 'executed TF32 flops (3 terms) of the dense blocks / step time; the pass is bound by the shared-memory '
-                          'pipe, not the tensor pipe (DESIGN.md 3.1b)'}
+            f16_peak, f16_src = 1400.0, 'B200_PROFILING.md fallback 1.4 PFLOP/s sustained bf16'
+        tensor = {'f16_tflops_achieved_over_the_step': flop / (ms_per_step * 1e-3) / 1e12, 'f16_peak_tflops': f16_peak,
+                  'frac': flop / (ms_per_step * 1e-3) / 1e12 / f16_peak, 'peak_source': f16_src,
+                  'note': 'executed fp16 flops (3 terms of the split) of the dense blocks / step time; the pass is bound by the '
+                          'serial chain of a sweep and the shared-memory pipe, not the tensor pipe (DESIGN.md 3.1b)'}
 
     line = {
         'metric': 'gates/s, random layered circuit', 'value': value, 'unit': 'gates/s', 'n_gpus': 1,

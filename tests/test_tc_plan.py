@@ -1,6 +1,6 @@
 """CPU-only: the tensor-core planner (qcs_plan_blocks plans a pass without launching it).
 
-A tensor-core sweep multiplies a run of gates into one dense 2^5 x 2^5 block; the host builds the two tf32 operand
+A tensor-core sweep multiplies a run of gates into one dense 2^5 x 2^5 block; the host builds the two fp16 operand
 images the kernel copies to shared memory.  Here the images are decoded and compared with the product of the same
 gates computed by the oracle (oracle/qc_oracle.py, apply_matrix_flat) on five qubits."""
 import ctypes
