@@ -156,3 +156,25 @@ def test_tail_trimming_never_reorders_non_commuting_gates(dtype, tc, monkeypatch
             c.append(qc.Operator.from_matrix(rand_unitary(rng, 3)), [int(q) for q in rng.permutation(n)[:3]])
         for tail_trim in (0, 4, 8, 12):
             assert _replay(c, dtype, tail_trim=tail_trim) < 1e-12, (trial, tail_trim)
+
+
+def test_leftover_last_pass_goes_back_into_the_pass_before():
+    """the hand-back of a short last sweep has nobody to hand to at the end of the circuit: a last pass of a few
+    leftover ops is merged into the pass before it when the planner holds the union (order still exact)"""
+    rng = np.random.default_rng(8)
+    for n, depth in ((14, 5), (16, 9), (13, 12)):
+        c = _layered(n, depth, seed=77 + n)
+        passes = c.schedule(np.complex64, fuse=True, max_ops=128)
+        order = [i for p in passes for i in p]
+        assert sorted(order) == list(range(len(c)))
+        vec = rand_state_vec(rng, n)
+        assert np.max(np.abs(_run_oracle(c, order, vec) - _run_oracle(c, range(len(c)), vec))) < 1e-12
+        if len(passes) >= 2 and len(passes[-1]) <= 8:
+            # a tiny last pass survives only if the planner refused the union
+            import ctypes
+            from qcircuits_b200 import _lib
+            from qcircuits_b200._device import make_ops
+            merged = passes[-2] + passes[-1]
+            ops, keep = make_ops([(c.gates[i].plan, c.gates[i].bits, False) for i in merged])
+            stats = (ctypes.c_int32 * 128)()
+            assert len(merged) > 128 or _lib.load().qcs_plan_stats(n, _lib.QCS_C64, ops, len(ops), stats) != 0
