@@ -14,15 +14,16 @@
 //   B (N, K): the block matrix in SHARED MEMORY, fp16, K-major, no swizzle, rows 0..31 = Re U, rows 32..63 = Im U; a
 //       "hi" and a "lo" image, built on the host from the float64 product of the gates (8 KB per block).
 //   D (M = 128, N = 64, fp32) in tensor memory: columns [Re out_0..31 | Im out_0..31], read back with tcgen05.ld by the
-//       same thread into the same registers (times 1 / s), which then go back to the tile in shared memory.
+//       same thread into the same registers, which then go back to the tile in shared memory (the tile stays ranged
+//       for the whole pass -- register ops are linear -- and 1 / s is folded into the factor of the store-out).
 //   Re out = Re a . Re U^T - Im a . Im U^T ,  Im out = Re a . Im U^T + Im a . Re U^T :
 //       per split term 2 instructions M128 N64 K16 (Re a against both halves of B) + 2 M128 N32 K16 with the b-negate
 //       flag (Im a against Im U, into the Re columns) + 2 M128 N32 K16 (Im a against Re U, into the Im columns);
 //       three terms, small ones first: lo.hi + hi.lo + hi.hi (the dropped lo.lo is 2^-24).  18 instructions per tile
 //       and sweep, half the tensor-pipe time and half the shared-memory operand reads of the tf32 form it replaced.
 // One elected lane issues the instructions after the group's barrier; completion comes back through
-// tcgen05.commit on an mbarrier.  A CTA is two groups of 256 threads that stream different tiles, so one group's
-// shared-memory and split work overlaps the other group's MMAs.
+// tcgen05.commit on an mbarrier.  A CTA is four groups of 128 threads (or two of 256) that stream different tiles, so
+// that the groups' shared-memory and split work overlaps each other's MMAs (tile_kernel_tc below).
 #pragma once
 #include <cuda_fp16.h>
 
