@@ -332,3 +332,22 @@ def test_sharded_dropin_state_over_gloo(world):
     assert np.max(np.abs(post - post_want.reshape(-1))) < 1e-12
     assert np.max(np.abs(res['kron_right'] - np.kron(want, res['phi']))) < 1e-12
     assert np.max(np.abs(res['kron_left'] - np.kron(res['phi'], want))) < 1e-12
+
+
+def test_norm_bound_is_kept_by_unitary_circuits_only():
+    """dist._all_unitary decides whether a sharded state keeps the device scalar that ranges the fp16 tensor-core
+    operands (qcs_apply_fused_bounded): every gate unitary -> kept; a projector or a scaled gate -> measured again"""
+    import qcircuits_b200 as qc
+    from qcircuits_b200.circuit import Circuit
+    from qcircuits_b200.dist import _all_unitary
+    c = Circuit(6)
+    c.append(qc.Hadamard(), [0])
+    c.append(qc.CNOT(), [0, 3])
+    c.append(qc.RotationZ(0.3), [5])
+    assert _all_unitary(c)
+    assert _all_unitary(c)                                   # (cached per gate count)
+    c.append(qc.Operator.from_matrix(np.array([[1, 0], [0, 0]], dtype=complex)), [2])
+    assert not _all_unitary(c)
+    c2 = Circuit(4)
+    c2.append(qc.Operator.from_matrix(2.0 * np.eye(2, dtype=complex)), [1])
+    assert not _all_unitary(c2)
